@@ -1,0 +1,163 @@
+/* orx.h -- C-ABI of liborx.so: the B200 (sm_100a) implementation of the openrec.tf2
+ * embedding-lookup -> pair-score -> loss -> sparse-gradient -> optimizer training step.
+ *
+ * The reference (ylongqi/openrec) is pure Python on TensorFlow and has NO FFI of its own;
+ * each entry point below therefore cites the reference *call site* (path:line relative to the
+ * reference repo) whose TensorFlow op sequence it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / CUDA types in signatures (orx_stream_t is a
+ *    cudaStream_t passed as void*; NULL = the legacy default stream);
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - the caller owns every buffer; the library allocates only the opaque per-device workspace
+ *    held by an orx_handle_t (index hash tables, duplicate-row gradient staging, id staging);
+ *  - all calls are asynchronous w.r.t. the host and ordered on the given stream;
+ *  - return value: ORX_OK (0) or a negative orx_status; orx_last_error_string() gives the
+ *    thread-local message.  There is no CPU fallback: without a CUDA device every compute
+ *    entry point fails with ORX_ERR_CUDA.
+ *  - tables are row-major float32 [rows, dim] with 64-bit row offsets; ids are int32.
+ */
+#ifndef ORX_H_
+#define ORX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORX_ABI_VERSION 1
+#define ORX_API __attribute__((visibility("default")))
+
+typedef struct orx_ctx* orx_handle_t;
+typedef void* orx_stream_t; /* cudaStream_t */
+
+enum orx_status {
+  ORX_OK = 0,
+  ORX_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unknown enum) */
+  ORX_ERR_CUDA = -2,        /* CUDA runtime error (message in orx_last_error_string) */
+  ORX_ERR_UNSUPPORTED = -3, /* combination not implemented */
+  ORX_ERR_NOMEM = -4        /* workspace allocation failed */
+};
+
+enum orx_pair_kind { ORX_PAIR_BPR = 0, ORX_PAIR_UCML = 1 };
+enum orx_point_kind { ORX_POINT_GMF = 0, ORX_POINT_WRMF = 1 };
+enum orx_score_kind { ORX_SCORE_DOT = 0, ORX_SCORE_NEG_SQDIST = 1 };
+
+/* Optimizers = the Keras OptimizerV2 sparse-apply semantics (dedup by row, then apply once):
+ *   SGD        var[r] -= lr*G
+ *   ADAGRAD    acc[r] += G^2; var[r] -= lr*G/(sqrt(acc[r])+eps)          (s0 = acc, init 0.1)
+ *   ADAM_LAZY  row-sparse Adam (NOT the reference's semantics; explicit opt-in)
+ *   ADAM_DENSE Keras-2.0 Adam on IndexedSlices: m,v decay and var update sweep the WHOLE table
+ *              every step (what `optimizers.Adam()` in tf2_examples/bpr_citeulike.py:31 does)
+ * For Adam s0 = m, s1 = v, lr_t = lr*sqrt(1-beta2^step)/(1-beta1^step), step is 1-based. */
+enum orx_opt_kind { ORX_OPT_SGD = 0, ORX_OPT_ADAGRAD = 1, ORX_OPT_ADAM_LAZY = 2, ORX_OPT_ADAM_DENSE = 3 };
+
+typedef struct {
+  int32_t kind; /* orx_opt_kind */
+  float lr, eps, beta1, beta2;
+  int64_t step; /* Adam: 1-based iteration count of THIS apply */
+} orx_opt_t;
+
+/* One LatentFactor (openrec/tf2/modules/latent_factor.py:4-15) and its optimizer slots. */
+typedef struct {
+  float* var;   /* [rows, dim] */
+  float* s0;    /* Adagrad accumulator | Adam m ; NULL for SGD */
+  float* s1;    /* Adam v ; NULL otherwise */
+  int64_t rows;
+  int32_t dim;
+} orx_table_t;
+
+/* ---- context ------------------------------------------------------------------------- */
+ORX_API int orx_abi_version(void);
+ORX_API const char* orx_last_error_string(void); /* host, thread-local */
+ORX_API int orx_create(int device, orx_handle_t* out);
+ORX_API int orx_destroy(orx_handle_t h);
+ORX_API int orx_device_count(int* n_out_host);
+/* Blocks the host until `stream` has drained (cudaStreamSynchronize). */
+ORX_API int orx_stream_synchronize(orx_handle_t h, orx_stream_t stream);
+
+/* ---- LatentFactor ---------------------------------------------------------------------- */
+/* LatentFactor.__init__ 'uniform' initializer = U(-0.05,0.05), on device, counter-based RNG
+ * (latent_factor.py:8-15).  lo/hi generalise it (glorot for MLP kernels). */
+ORX_API int orx_fill_uniform(orx_handle_t h, float* dst, int64_t n, float lo, float hi, uint64_t seed, orx_stream_t s);
+/* LatentFactor.__call__ = Embedding.call: out[b,:] = tab[ids[b],:] (bpr.py:23-27, dlrm.py:83-85).
+ * ids int32 (id_is_i64 = 0) or int64 (1).  Out-of-range ids yield zero rows and are counted in
+ * *n_bad (device int32, may be NULL). */
+ORX_API int orx_gather(orx_handle_t h, const float* tab, int64_t rows, int32_t dim, const void* ids, int32_t id_is_i64,
+               int64_t n, float* out, int32_t* n_bad, orx_stream_t s);
+/* LatentFactor.censor (latent_factor.py:17-23): for the UNIQUE ids, row /= max(||row||_2, min_norm). */
+ORX_API int orx_censor(orx_handle_t h, float* tab, int64_t rows, int32_t dim, const int32_t* ids, int32_t n,
+               float min_norm, orx_stream_t s);
+
+/* ---- pairwise recommenders: BPR (recommenders/bpr.py:21-37 + modules/pairwise_log_loss.py:15-34)
+ *      and UCML (recommenders/ucml.py:21-42) ------------------------------------------------
+ * One training step == model(u,p,n) under GradientTape -> tape.gradient(c_loss*loss + c_l2*l2_loss)
+ * -> optimizer.apply_gradients (tf2_examples/bpr_citeulike.py:33-39; the example passes the tuple
+ * (loss, l2_loss) => c_loss = c_l2 = 1).  All rows are gathered from the PRE-step tables, duplicate
+ * rows' gradients are summed, the optimizer is applied once per unique row.
+ * out4 (device float[4]) = { loss, l2_loss, number of out-of-range ids, number of staged rows }.
+ * user/item must have equal dim; item_bias has dim 1 and item.rows rows. */
+ORX_API int orx_pairwise_step(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                      const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
+                      int32_t B, float margin, float c_loss, float c_l2, const orx_opt_t* opt_host,
+                      float* out4, orx_stream_t s);
+/* Same step through HOST buffers: ids are copied host->device (pinned memory recommended) and out4 is
+ * copied device->host on `s`, all inside this call's stream work (the bench's end-to-end arm). */
+ORX_API int orx_pairwise_step_host(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                           const orx_table_t* item_bias, const int32_t* uid_host, const int32_t* pid_host,
+                           const int32_t* nid_host, int32_t B, float margin, float c_loss, float c_l2,
+                           const orx_opt_t* opt_host, float* out4_host, orx_stream_t s);
+/* Forward only: (loss, l2_loss) -> out4[0..1]  (model(u,p,n) without a tape). */
+ORX_API int orx_pairwise_fwd(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                     const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
+                     int32_t B, float margin, float* out4, orx_stream_t s);
+/* Un-fused gradients in TF IndexedSlices form (values per lookup, NOT deduplicated):
+ * d_user[B,D], d_pos[B,D], d_neg[B,D], d_bp[B], d_bn[B]; any may be NULL.  g_out[B] (optional) receives
+ * the per-triplet loss-gradient scalar. */
+ORX_API int orx_pairwise_grad(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                      const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
+                      int32_t B, float margin, float c_loss, float c_l2, float* d_user, float* d_pos, float* d_neg,
+                      float* d_bp, float* d_bn, float* g_out, orx_stream_t s);
+
+/* ---- pointwise recommenders: GMF (recommenders/gmf.py:22-34) and WRMF (recommenders/wrmf.py:21-34 +
+ *      modules/pointwise_mse_loss.py:18-31) ---------------------------------------------------
+ * GMF: w = the [D] kernel of Dense(1,use_bias=False) (gmf.py:19) as a 1-row orx_table_t (rows=1, dim=D);
+ * WRMF: w = NULL, (a,b) label weights, use_sigmoid as PointwiseMSELoss(sigmoid=...). */
+ORX_API int orx_pointwise_step(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                       const orx_table_t* item_bias, const orx_table_t* w, const int32_t* uid, const int32_t* iid,
+                       const float* label, int32_t B, float a, float b, int32_t use_sigmoid, float c_loss,
+                       float c_l2, const orx_opt_t* opt_host, float* out4, orx_stream_t s);
+ORX_API int orx_pointwise_fwd(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                      const orx_table_t* item_bias, const orx_table_t* w, const int32_t* uid, const int32_t* iid,
+                      const float* label, int32_t B, float a, float b, int32_t use_sigmoid, float* out4,
+                      orx_stream_t s);
+ORX_API int orx_pointwise_grad(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                       const orx_table_t* item_bias, const orx_table_t* w, const int32_t* uid, const int32_t* iid,
+                       const float* label, int32_t B, float a, float b, int32_t use_sigmoid, float c_loss,
+                       float c_l2, float* d_user, float* d_item, float* d_bias, float* d_w, float* g_out,
+                       orx_stream_t s);
+
+/* ---- dense variables (GMF w, MLP kernels/biases): Keras dense apply ---------------------- */
+ORX_API int orx_dense_apply(orx_handle_t h, float* var, float* s0, float* s1, const float* grad, int64_t n,
+                    const orx_opt_t* opt_host, orx_stream_t s);
+
+/* ---- inference: full-catalogue scoring (bpr.py:39-43, wrmf.py:36-40, ucml.py:50-53, gmf.py:36-41)
+ * scores[Bu, I] = user_rows . item^T + bias   (DOT; GMF passes user_rows pre-multiplied by w via `scale`)
+ *               = -||user_row - item||^2 + bias (NEG_SQDIST).  scale may be NULL. */
+ORX_API int orx_score_all(orx_handle_t h, int32_t kind, const float* user_tab, int64_t U, const int32_t* uid, int32_t Bu,
+                  const float* scale, const float* item_tab, const float* item_bias, int64_t I, int32_t dim,
+                  float* scores, orx_stream_t s);
+
+/* ---- ranking metrics (openrec/tf2/metrics/ranking_metrics.py:8-69), one row per user --------
+ * pos/excl are uint8 masks [R, I]; at[] (host) the cut-offs; outputs auc[R], ndcg[R,n_at], recall[R,n_at]
+ * (any may be NULL). */
+ORX_API int orx_rank_metrics(orx_handle_t h, const float* pred, const uint8_t* pos, const uint8_t* excl, int32_t R,
+                     int64_t I, const int32_t* at_host, int32_t n_at, float* auc, float* ndcg, float* recall,
+                     orx_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORX_H_ */

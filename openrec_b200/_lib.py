@@ -1,0 +1,86 @@
+"""ctypes binding of liborx.so (declared in include/orx.h).
+
+There is NO CPU fallback: if the shared library is missing this module raises at import of
+the first symbol; if no CUDA device is present every compute entry point returns ORX_ERR_CUDA,
+which `check` turns into a RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "liborx.so")
+
+ORX_PAIR_BPR, ORX_PAIR_UCML = 0, 1
+ORX_POINT_GMF, ORX_POINT_WRMF = 0, 1
+ORX_SCORE_DOT, ORX_SCORE_NEG_SQDIST = 0, 1
+ORX_OPT_SGD, ORX_OPT_ADAGRAD, ORX_OPT_ADAM_LAZY, ORX_OPT_ADAM_DENSE = 0, 1, 2, 3
+
+
+class OrxOpt(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("lr", C.c_float), ("eps", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("step", C.c_int64)]
+
+
+class OrxTable(C.Structure):
+    _fields_ = [("var", C.c_void_p), ("s0", C.c_void_p), ("s1", C.c_void_p), ("rows", C.c_int64),
+                ("dim", C.c_int32)]
+
+
+_vp, _i32, _i64, _f, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
+_T = C.POINTER(OrxTable)
+_O = C.POINTER(OrxOpt)
+
+# name -> argtypes (restype is int unless noted); mirrors include/orx.h one to one
+SIGNATURES = {
+    "orx_abi_version": [],
+    "orx_last_error_string": [],
+    "orx_create": [C.c_int, C.POINTER(_vp)],
+    "orx_destroy": [_vp],
+    "orx_device_count": [C.POINTER(C.c_int)],
+    "orx_stream_synchronize": [_vp, _vp],
+    "orx_fill_uniform": [_vp, _vp, _i64, _f, _f, _u64, _vp],
+    "orx_gather": [_vp, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
+    "orx_censor": [_vp, _vp, _i64, _i32, _vp, _i32, _f, _vp],
+    "orx_pairwise_step": [_vp, _i32, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _f, _O, _vp, _vp],
+    "orx_pairwise_step_host": [_vp, _i32, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _f, _O, _vp, _vp],
+    "orx_pairwise_fwd": [_vp, _i32, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _vp, _vp],
+    "orx_pairwise_grad": [_vp, _i32, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "orx_pointwise_step": [_vp, _i32, _T, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _i32, _f, _f, _O, _vp, _vp],
+    "orx_pointwise_fwd": [_vp, _i32, _T, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _i32, _vp, _vp],
+    "orx_pointwise_grad": [_vp, _i32, _T, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _i32, _f, _f,
+                           _vp, _vp, _vp, _vp, _vp, _vp],
+    "orx_dense_apply": [_vp, _vp, _vp, _vp, _vp, _i64, _O, _vp],
+    "orx_score_all": [_vp, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
+    "orx_rank_metrics": [_vp, _vp, _vp, _vp, _i32, _i64, C.POINTER(_i32), _i32, _vp, _vp, _vp, _vp],
+}
+
+_lib = None
+
+
+def lib():
+    """Load liborx.so once.  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"liborx.so not found at {LIB_PATH}: build it with `python -m openrec_b200.build` "
+                "(there is no CPU fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_char_p if name == "orx_last_error_string" else C.c_int
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    s = lib().orx_last_error_string()
+    return s.decode() if s else ""
+
+
+def check(rc: int, what: str = "liborx"):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (status {rc}): {last_error()}")

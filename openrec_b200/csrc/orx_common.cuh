@@ -1,0 +1,216 @@
+// orx_common.cuh -- shared host/device helpers for liborx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/orx.h"
+
+// ---------------------------------------------------------------------------------------
+// host: errors + context
+// ---------------------------------------------------------------------------------------
+void orx_set_error(const char* fmt, ...);
+
+#define ORX_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      orx_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+      return ORX_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define ORX_REQUIRE(cond, msg)                                  \
+  do {                                                          \
+    if (!(cond)) {                                              \
+      orx_set_error("%s: %s", __func__, msg);                   \
+      return ORX_ERR_INVALID;                                   \
+    }                                                           \
+  } while (0)
+
+#define ORX_LAUNCH_CHECK() ORX_CUDA(cudaGetLastError())
+
+// Open-addressing hash index over the ids of one table for one batch ("K9").
+// slot word: high 32 = occurrence count, low 32 = id+1 (0 = empty).
+struct OrxHash {
+  unsigned long long* slots;  // [cap]
+  int32_t* didx;              // [cap]  compact staging index of a staged row
+  int32_t* did;               // [cap_rows] row id of staging index d
+  int32_t* counter;           // number of staged rows
+  uint32_t mask;
+  int32_t shift;  // 32 - log2(cap)
+};
+
+struct orx_ctx {
+  int device;
+  int num_sms;
+  // index workspace (sized for cap_B lookups per table side)
+  int64_t cap_B;  // largest batch the workspace is sized for
+  OrxHash hu, hi;
+  int32_t* counters;  // [8]: 0 staged_u, 1 staged_i, 2 ticket, 3 bad ids, 4.. spare
+  // staged-row gradient buffers
+  float *gu, *gi, *gb, *gw;
+  int64_t g_rows_u, g_rows_i;
+  int32_t g_dim;
+  // loss partials
+  float* partials;  // [cap_partials*2]
+  int32_t cap_partials;
+  // id staging for the *_host entry points (double buffered)
+  int32_t* ids_stage[2];
+  float* out_stage[2];
+  int64_t stage_cap;
+  uint32_t stage_flip;
+};
+
+int orx_ensure_workspace(orx_ctx* c, int64_t B, int32_t dim, bool full_staging);
+int orx_ensure_stage(orx_ctx* c, int64_t n_ints);
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+struct OrxOptDev {
+  int32_t kind;
+  float lr;    // SGD/Adagrad: lr ; Adam: bias-corrected lr_t
+  float eps, beta1, beta2;
+};
+
+#ifdef __CUDACC__
+
+#define ORX_FULL 0xffffffffu
+
+__device__ __forceinline__ uint32_t orx_hash32(uint32_t id, int shift) { return (id * 2654435769u) >> shift; }
+
+// Insert one id.  mode 0: rows get a staging index on their SECOND occurrence (duplicates only);
+// mode 1: on the FIRST occurrence (ADAM_DENSE stages every row); mode 2: never (pure dedup, censor).
+// Returns the pre-insert occurrence count.
+__device__ __forceinline__ uint32_t orx_hash_insert(const OrxHash& t, int32_t id, int mode) {
+  const uint32_t key = (uint32_t)id + 1u;
+  uint32_t h = orx_hash32((uint32_t)id, t.shift);
+  while (true) {
+    unsigned long long w = __ldcg(t.slots + h);
+    if ((uint32_t)w == 0u) {
+      unsigned long long old = atomicCAS(t.slots + h, 0ull, (1ull << 32) | key);
+      if (old == 0ull) {
+        if (mode == 1) {
+          int d = atomicAdd(t.counter, 1);
+          t.didx[h] = d;
+          t.did[d] = id;
+        }
+        return 0u;
+      }
+      w = old;
+    }
+    if ((uint32_t)w == key) {
+      unsigned long long old = atomicAdd(t.slots + h, 1ull << 32);
+      uint32_t c = (uint32_t)(old >> 32);
+      if (mode == 0 && c == 1u) {
+        int d = atomicAdd(t.counter, 1);
+        t.didx[h] = d;
+        t.did[d] = id;
+      }
+      return c;
+    }
+    h = (h + 1) & t.mask;
+  }
+}
+
+// Lookup an id known to be present.  Returns count; *d = staging index when count>1 || stage_all.
+__device__ __forceinline__ uint32_t orx_hash_find(const OrxHash& t, int32_t id, int32_t* d) {
+  const uint32_t key = (uint32_t)id + 1u;
+  uint32_t h = orx_hash32((uint32_t)id, t.shift);
+  while (true) {
+    unsigned long long w = __ldg(t.slots + h);
+    if ((uint32_t)w == key) {
+      *d = __ldg(t.didx + h);
+      return (uint32_t)(w >> 32);
+    }
+    if ((uint32_t)w == 0u) {
+      *d = -1;
+      return 0u;
+    }
+    h = (h + 1) & t.mask;
+  }
+}
+
+template <int W>
+__device__ __forceinline__ float orx_group_sum(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(ORX_FULL, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 orx_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void orx_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// one 128-bit fire-and-forget reduction (REDG.E.ADD.F32x4 on sm_90+)
+__device__ __forceinline__ void orx_red4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// log(sigmoid(y)) and sigmoid(-y), the stable forms TF uses.
+__device__ __forceinline__ void orx_logsig(float y, float* logsig, float* sig_neg) {
+  float e = expf(-fabsf(y));
+  *logsig = fminf(y, 0.f) - log1pf(e);
+  *sig_neg = (y >= 0.f) ? e / (1.f + e) : 1.f / (1.f + e);
+}
+__device__ __forceinline__ float orx_sigmoid(float y) {
+  float e = expf(-fabsf(y));
+  return (y >= 0.f) ? 1.f / (1.f + e) : e / (1.f + e);
+}
+
+
+// One optimizer update of one scalar.  OPT is an orx_opt_kind (ADAM_DENSE never reaches here:
+// its rows are staged and swept).
+template <int OPT>
+__device__ __forceinline__ float orx_apply(float w, float g, float& s0, float& s1, const OrxOptDev& o) {
+  if (OPT == ORX_OPT_SGD) {
+    return w - o.lr * g;
+  } else if (OPT == ORX_OPT_ADAGRAD) {
+    s0 = s0 + g * g;
+    return w - o.lr * g / (sqrtf(s0) + o.eps);
+  } else {
+    s0 = o.beta1 * s0 + (1.f - o.beta1) * g;
+    s1 = o.beta2 * s1 + (1.f - o.beta2) * g * g;
+    return w - o.lr * s0 / (sqrtf(s1) + o.eps);
+  }
+}
+
+template <int OPT>
+__device__ __forceinline__ float4 orx_apply4(float4 w, float4 g, float4& s0, float4& s1, const OrxOptDev& o) {
+  float4 r;
+  r.x = orx_apply<OPT>(w.x, g.x, s0.x, s1.x, o);
+  r.y = orx_apply<OPT>(w.y, g.y, s0.y, s1.y, o);
+  r.z = orx_apply<OPT>(w.z, g.z, s0.z, s1.z, o);
+  r.w = orx_apply<OPT>(w.w, g.w, s0.w, s1.w, o);
+  return r;
+}
+
+#endif  // __CUDACC__
+
+// Arguments of the shared tail kernel (staged rows -> optimizer, hash clear, loss reduction).
+struct TailArgs {
+  float *U, *Us0, *Us1;
+  float *I, *Is0, *Is1;
+  float *Bv, *Bs0, *Bs1;
+  int D;
+  OrxOptDev opt;
+  OrxHash hu, hi;
+  float *gu, *gi, *gb;
+  const float* partials;
+  int n_partials;
+  float loss_scale;  // BPR: 1/B (mean), UCML: 1 (sum)
+  int32_t* counters;
+  float* out4;
+  // GMF dense weight (pointwise tail only)
+  float *W, *Ws0, *Ws1, *gw;
+  float c_l2;
+};
+
+OrxOptDev orx_opt_to_dev(const orx_opt_t* o);
+int orx_launch_tail(orx_ctx* c, const TailArgs& ta, int opt_kind, cudaStream_t st);
+int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t rows, int D, const OrxHash& h,
+                          const float* gstage, const OrxOptDev& o, cudaStream_t st);
+int orx_ensure_partials(orx_ctx* c, int need, cudaStream_t st);
+int orx_launch_reduce_partials(const float* partials, int n, float loss_scale, float* out4, cudaStream_t st);
+int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
+                           const int32_t* b1, int64_t rows_b, int32_t nb, bool stage_all, cudaStream_t st);

@@ -1,0 +1,173 @@
+// orx_ctx.cu -- context, workspace and error plumbing of liborx.
+#include <stdarg.h>
+#include <string.h>
+
+#include "orx_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void orx_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* orx_last_error_string(void) { return g_err; }
+extern "C" int orx_abi_version(void) { return ORX_ABI_VERSION; }
+
+extern "C" int orx_device_count(int* n) {
+  ORX_REQUIRE(n != nullptr, "null output");
+  *n = 0;
+  ORX_CUDA(cudaGetDeviceCount(n));
+  return ORX_OK;
+}
+
+static void free_hash(OrxHash& t) {
+  cudaFree(t.slots);
+  cudaFree(t.didx);
+  cudaFree(t.did);
+  t.slots = nullptr;
+  t.didx = nullptr;
+  t.did = nullptr;
+}
+
+static void free_workspace(orx_ctx* c) {
+  free_hash(c->hu);
+  free_hash(c->hi);
+  cudaFree(c->gu);
+  cudaFree(c->gi);
+  cudaFree(c->gb);
+  cudaFree(c->gw);
+  c->gu = c->gi = c->gb = c->gw = nullptr;
+  c->cap_B = 0;
+  c->g_dim = 0;
+}
+
+static uint32_t pow2_at_least(int64_t n) {
+  uint32_t p = 1024;
+  while ((int64_t)p < n) p <<= 1;
+  return p;
+}
+
+static int alloc_hash(OrxHash& t, int64_t lookups, int32_t* counter) {
+  uint32_t cap = pow2_at_least(2 * lookups);
+  int lg = 0;
+  while ((1u << lg) < cap) ++lg;
+  t.mask = cap - 1;
+  t.shift = 32 - lg;
+  t.counter = counter;
+  ORX_CUDA(cudaMalloc(&t.slots, sizeof(unsigned long long) * cap));
+  ORX_CUDA(cudaMalloc(&t.didx, sizeof(int32_t) * cap));
+  ORX_CUDA(cudaMalloc(&t.did, sizeof(int32_t) * (lookups + 1)));
+  ORX_CUDA(cudaMemset(t.slots, 0, sizeof(unsigned long long) * cap));
+  return ORX_OK;
+}
+
+// Workspace is sized for B lookups on the user side and 2B on the item side; every lookup may be
+// staged (ADAM_DENSE stages all rows), so the staging buffers hold B resp. 2B rows of `dim` floats.
+int orx_ensure_workspace(orx_ctx* c, int64_t B, int32_t dim, bool /*full_staging*/) {
+  if (B <= c->cap_B && dim <= c->g_dim) return ORX_OK;
+  int64_t nb = B > c->cap_B ? B : c->cap_B;
+  int32_t nd = dim > c->g_dim ? dim : c->g_dim;
+  ORX_CUDA(cudaDeviceSynchronize());
+  free_workspace(c);
+  int rc;
+  if ((rc = alloc_hash(c->hu, nb, c->counters + 0)) != ORX_OK) return rc;
+  if ((rc = alloc_hash(c->hi, 2 * nb, c->counters + 1)) != ORX_OK) return rc;
+  c->g_rows_u = nb;
+  c->g_rows_i = 2 * nb;
+  size_t bu = sizeof(float) * (size_t)c->g_rows_u * nd, bi = sizeof(float) * (size_t)c->g_rows_i * nd;
+  ORX_CUDA(cudaMalloc(&c->gu, bu));
+  ORX_CUDA(cudaMalloc(&c->gi, bi));
+  ORX_CUDA(cudaMalloc(&c->gb, sizeof(float) * (size_t)c->g_rows_i));
+  ORX_CUDA(cudaMalloc(&c->gw, sizeof(float) * (size_t)nd));
+  ORX_CUDA(cudaMemset(c->gu, 0, bu));
+  ORX_CUDA(cudaMemset(c->gi, 0, bi));
+  ORX_CUDA(cudaMemset(c->gb, 0, sizeof(float) * (size_t)c->g_rows_i));
+  ORX_CUDA(cudaMemset(c->gw, 0, sizeof(float) * (size_t)nd));
+  ORX_CUDA(cudaMemset(c->counters, 0, sizeof(int32_t) * 8));
+  c->cap_B = nb;
+  c->g_dim = nd;
+  return ORX_OK;
+}
+
+int orx_ensure_stage(orx_ctx* c, int64_t n_ints) {
+  if (n_ints <= c->stage_cap) return ORX_OK;
+  ORX_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(c->ids_stage[i]);
+    c->ids_stage[i] = nullptr;
+    ORX_CUDA(cudaMalloc(&c->ids_stage[i], sizeof(int32_t) * (size_t)n_ints));
+  }
+  c->stage_cap = n_ints;
+  return ORX_OK;
+}
+
+extern "C" int orx_create(int device, orx_handle_t* out) {
+  ORX_REQUIRE(out != nullptr, "null output handle");
+  *out = nullptr;
+  int n = 0;
+  ORX_CUDA(cudaGetDeviceCount(&n));
+  ORX_REQUIRE(device >= 0 && device < n, "device ordinal out of range");
+  ORX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ORX_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    orx_set_error("orx_create: liborx is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+                  prop.minor);
+    return ORX_ERR_UNSUPPORTED;
+  }
+  orx_ctx* c = new orx_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->cap_partials = c->num_sms * 64;
+  if (cudaMalloc(&c->counters, sizeof(int32_t) * 8) != cudaSuccess ||
+      cudaMalloc(&c->partials, sizeof(float) * 2 * (size_t)c->cap_partials) != cudaSuccess ||
+      cudaMalloc(&c->out_stage[0], sizeof(float) * 8) != cudaSuccess ||
+      cudaMalloc(&c->out_stage[1], sizeof(float) * 8) != cudaSuccess) {
+    orx_set_error("orx_create: workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return ORX_ERR_NOMEM;
+  }
+  cudaMemset(c->counters, 0, sizeof(int32_t) * 8);
+  *out = c;
+  return ORX_OK;
+}
+
+extern "C" int orx_destroy(orx_handle_t h) {
+  if (!h) return ORX_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_workspace(h);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->ids_stage[i]);
+    cudaFree(h->out_stage[i]);
+  }
+  cudaFree(h->counters);
+  cudaFree(h->partials);
+  delete h;
+  return ORX_OK;
+}
+
+extern "C" int orx_stream_synchronize(orx_handle_t h, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr, "null handle");
+  ORX_CUDA(cudaStreamSynchronize((cudaStream_t)s));
+  return ORX_OK;
+}
+
+OrxOptDev orx_opt_to_dev(const orx_opt_t* o) {
+  OrxOptDev d;
+  d.kind = o->kind;
+  d.lr = o->lr;
+  d.eps = o->eps;
+  d.beta1 = o->beta1;
+  d.beta2 = o->beta2;
+  if (o->kind == ORX_OPT_ADAM_LAZY || o->kind == ORX_OPT_ADAM_DENSE) {
+    // lr_t = lr*sqrt(1-b2^t)/(1-b1^t), evaluated in double like the oracle's adam_lr_t
+    double t = (double)(o->step < 1 ? 1 : o->step);
+    d.lr = (float)((double)o->lr * sqrt(1.0 - pow((double)o->beta2, t)) / (1.0 - pow((double)o->beta1, t)));
+  }
+  return d;
+}

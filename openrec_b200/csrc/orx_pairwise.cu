@@ -1,0 +1,901 @@
+// orx_pairwise.cu -- BPR / UCML fused training step (K1/K2), its batch index (K9) and tail.
+//
+// Reference path replaced (paths relative to the reference repo):
+//   openrec/tf2/recommenders/bpr.py:21-37, ucml.py:21-42, modules/pairwise_log_loss.py:15-34
+//   + tape.gradient + optimizer.apply_gradients (tf2_examples/bpr_citeulike.py:33-39).
+//
+// Synchronous-batch semantics in three launches on one stream:
+//   1. k_index_build : hash every id of the batch; rows hit more than once get a "staging" slot.
+//   2. k_pair_step   : per triplet gather u,p,n (128-bit loads), score, loss, per-sample gradient.
+//        * a row referenced exactly once in the batch is owned by its triplet: optimizer applied
+//          in registers, row + slots written back once (read once, written once == algorithmic bytes);
+//        * a row referenced more than once is NEVER written here: its per-sample gradient is
+//          red.global.add'ed into the compact staging buffer (so every gather sees pre-step values).
+//   3. k_pair_tail   : optimizer for the staged rows (once per unique row), staging re-zeroed,
+//                      hash cleared, deterministic loss reduction.
+#include "orx_common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// K9: batch index
+// ---------------------------------------------------------------------------------------
+__global__ void k_index_build(OrxHash hu, OrxHash hi, const int32_t* __restrict__ a, int64_t rows_a, int na,
+                              const int32_t* __restrict__ b0, const int32_t* __restrict__ b1, int64_t rows_b, int nb,
+                              int stage_all, int32_t* bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = na + (b1 ? 2 * nb : nb);
+  if (i >= total) return;
+  if (i < na) {
+    const int32_t id = a[i];
+    if (id >= 0 && (int64_t)id < rows_a) orx_hash_insert(hu, id, stage_all);
+    else atomicAdd(bad, 1);
+  } else {
+    const int j = i - na;
+    const int32_t id = j < nb ? b0[j] : b1[j - nb];
+    if (id >= 0 && (int64_t)id < rows_b) orx_hash_insert(hi, id, stage_all);
+    else atomicAdd(bad, 1);
+  }
+}
+
+int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
+                           const int32_t* b1, int64_t rows_b, int32_t nb, bool stage_all, cudaStream_t st) {
+  const int total = na + (b1 ? 2 * nb : nb);
+  if (total <= 0) return ORX_OK;
+  k_index_build<<<(total + 255) / 256, 256, 0, st>>>(c->hu, c->hi, a, rows_a, na, b0, b1, rows_b, nb,
+                                                    stage_all ? 1 : 0, c->counters + 3);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1/K2: fused step
+// ---------------------------------------------------------------------------------------
+struct PairArgs {
+  float *U, *Us0, *Us1;
+  float *I, *Is0, *Is1;
+  float *Bv, *Bs0, *Bs1;
+  int64_t rowsU, rowsI;
+  int D;
+  const int32_t *uid, *pid, *nid;
+  int B;
+  float margin, c_loss, c_l2, inv_B;
+  OrxOptDev opt;
+  OrxHash hu, hi;
+  float *gu, *gi, *gb;
+  float* partials;
+  float* g_out;
+};
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float sqd4(float4 a, float4 b) {
+  float x = a.x - b.x, y = a.y - b.y, z = a.z - b.z, w = a.w - b.w;
+  return x * x + y * y + z * z + w * w;
+}
+// r = s*(a-b) + c*d
+__device__ __forceinline__ float4 axmb_pcd(float s, float4 a, float4 b, float c, float4 d) {
+  return make_float4(s * (a.x - b.x) + c * d.x, s * (a.y - b.y) + c * d.y, s * (a.z - b.z) + c * d.z,
+                     s * (a.w - b.w) + c * d.w);
+}
+// r = s*a + c*d
+__device__ __forceinline__ float4 sa_pcd(float s, float4 a, float c, float4 d) {
+  return make_float4(s * a.x + c * d.x, s * a.y + c * d.y, s * a.z + c * d.z, s * a.w + c * d.w);
+}
+
+// Per-sample score -> (loss term, gradient scalars).  BPR: x = (u.p+bp)-(u.n+bn),
+// loss term = -log sigmoid(max(x,-30)), g = -(c_loss/B) sigmoid(-y) [x>=-30]  (pairwise_log_loss.py:19-32).
+// UCML: h = margin - ((-|u-p|^2+bp) - (-|u-n|^2+bn)), loss term = max(h,0), a = c_loss [h>=0] (ucml.py:29-39).
+template <int KIND>
+__device__ __forceinline__ void pair_score(float s1, float s2, float bp, float bn, const PairArgs& a,
+                                           float* loss_term, float* g) {
+  if (KIND == ORX_PAIR_BPR) {
+    const float x = (s1 + bp) - (s2 + bn);
+    const float y = fmaxf(x, -30.f);
+    float ls, sn;
+    orx_logsig(y, &ls, &sn);
+    *loss_term = -ls;
+    *g = (x >= -30.f) ? -(a.c_loss * a.inv_B) * sn : 0.f;
+  } else {
+    const float h = a.margin - (((-s1) + bp) - ((-s2) + bn));
+    *loss_term = fmaxf(h, 0.f);
+    *g = (h >= 0.f) ? a.c_loss : 0.f;
+  }
+}
+
+// Row gradients from the scalar.
+template <int KIND>
+__device__ __forceinline__ void pair_row_grads(float g, float c2, float4 u, float4 p, float4 n, float4* gu,
+                                               float4* gp, float4* gn) {
+  if (KIND == ORX_PAIR_BPR) {
+    *gu = axmb_pcd(g, p, n, c2, u);
+    *gp = sa_pcd(g, u, c2, p);
+    *gn = sa_pcd(-g, u, c2, n);
+  } else {
+    const float t = 2.f * g;
+    *gu = axmb_pcd(t, n, p, c2, u);
+    *gp = axmb_pcd(t, p, u, c2, p);
+    *gn = axmb_pcd(t, u, n, c2, n);
+  }
+}
+
+template <int K, bool S0, bool S1>
+struct TripRegs {
+  float4 u[K], p[K], n[K];
+  float4 us0[K], ps0[K], ns0[K];  // dead arrays are eliminated when the optimizer has no such slot
+  float4 us1[K], ps1[K], ns1[K];
+  int fl, uu, pp, nn, du, dp, dn;
+  float bp, bn;
+};
+
+// flags: bit0 triplet valid, bit1/2/3 user/pos/neg row owned by this triplet (fast path)
+template <int KIND, int OPT, int D, int CH>
+__global__ void __launch_bounds__(256) k_pair_step(const PairArgs a) {
+  constexpr int G = (D / 4 < 32) ? D / 4 : 32;  // lanes per triplet
+  constexpr int K = D / (4 * G);                // float4 per lane per row
+  constexpr int TPW = 32 / G;                   // triplets in flight per warp
+  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool STAGE_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
+  constexpr bool PIPE = !S1;  // register double-buffering (too many registers with Adam's 9 rows)
+  static_assert(CH % TPW == 0, "chunk must be a multiple of the triplets per warp");
+  typedef TripRegs<K, S0, S1> Regs;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int grp = lane / G, gl = lane % G;
+  const int t = warp * CH + lane;
+
+  // ---- per-lane metadata of triplet t (lanes < CH)
+  int u_id = 0, p_id = 0, n_id = 0, du = -1, dp = -1, dn = -1, flags = 0;
+  float bp = 0.f, bn = 0.f, bps0 = 0.f, bps1 = 0.f, bns0 = 0.f, bns1 = 0.f;
+  if (lane < CH && t < a.B) {
+    u_id = a.uid[t];
+    p_id = a.pid[t];
+    n_id = a.nid[t];
+    const bool ok = u_id >= 0 && u_id < a.rowsU && p_id >= 0 && p_id < a.rowsI && n_id >= 0 && n_id < a.rowsI;
+    if (ok) {
+      const uint32_t cu = orx_hash_find(a.hu, u_id, &du);
+      const uint32_t cp = orx_hash_find(a.hi, p_id, &dp);
+      const uint32_t cn = orx_hash_find(a.hi, n_id, &dn);
+      bp = __ldcg(a.Bv + p_id);
+      bn = __ldcg(a.Bv + n_id);
+      flags = 1;
+      if (!STAGE_ONLY) {
+        flags |= (cu == 1u ? 2 : 0) | (cp == 1u ? 4 : 0) | (cn == 1u ? 8 : 0);
+        if (S0) {
+          if (flags & 4) bps0 = __ldcg(a.Bs0 + p_id);
+          if (flags & 8) bns0 = __ldcg(a.Bs0 + n_id);
+        }
+        if (S1) {
+          if (flags & 4) bps1 = __ldcg(a.Bs1 + p_id);
+          if (flags & 8) bns1 = __ldcg(a.Bs1 + n_id);
+        }
+      }
+    }
+  }
+
+  auto load = [&](int j, Regs& r) {
+    const int src = j + grp;
+    r.fl = __shfl_sync(ORX_FULL, flags, src);
+    r.uu = __shfl_sync(ORX_FULL, u_id, src);
+    r.pp = __shfl_sync(ORX_FULL, p_id, src);
+    r.nn = __shfl_sync(ORX_FULL, n_id, src);
+    r.du = __shfl_sync(ORX_FULL, du, src);
+    r.dp = __shfl_sync(ORX_FULL, dp, src);
+    r.dn = __shfl_sync(ORX_FULL, dn, src);
+    r.bp = __shfl_sync(ORX_FULL, bp, src);
+    r.bn = __shfl_sync(ORX_FULL, bn, src);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int off = (k * G + gl) * 4;
+      const bool v = r.fl & 1;
+      r.u[k] = v ? __ldcg(reinterpret_cast<const float4*>(a.U + (int64_t)r.uu * D + off)) : z;
+      r.p[k] = v ? __ldcg(reinterpret_cast<const float4*>(a.I + (int64_t)r.pp * D + off)) : z;
+      r.n[k] = v ? __ldcg(reinterpret_cast<const float4*>(a.I + (int64_t)r.nn * D + off)) : z;
+      if (S0) {
+        r.us0[k] = (r.fl & 2) ? __ldcg(reinterpret_cast<const float4*>(a.Us0 + (int64_t)r.uu * D + off)) : z;
+        r.ps0[k] = (r.fl & 4) ? __ldcg(reinterpret_cast<const float4*>(a.Is0 + (int64_t)r.pp * D + off)) : z;
+        r.ns0[k] = (r.fl & 8) ? __ldcg(reinterpret_cast<const float4*>(a.Is0 + (int64_t)r.nn * D + off)) : z;
+      }
+      if (S1) {
+        r.us1[k] = (r.fl & 2) ? __ldcg(reinterpret_cast<const float4*>(a.Us1 + (int64_t)r.uu * D + off)) : z;
+        r.ps1[k] = (r.fl & 4) ? __ldcg(reinterpret_cast<const float4*>(a.Is1 + (int64_t)r.pp * D + off)) : z;
+        r.ns1[k] = (r.fl & 8) ? __ldcg(reinterpret_cast<const float4*>(a.Is1 + (int64_t)r.nn * D + off)) : z;
+      }
+    }
+  };
+
+  float loss_acc = 0.f, l2_acc = 0.f, g_own = 0.f;
+
+  auto process = [&](int j, Regs& r) {
+    float s1 = 0.f, s2 = 0.f, sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (KIND == ORX_PAIR_BPR) {
+        s1 += dot4(r.u[k], r.p[k]);
+        s2 += dot4(r.u[k], r.n[k]);
+      } else {
+        s1 += sqd4(r.u[k], r.p[k]);
+        s2 += sqd4(r.u[k], r.n[k]);
+      }
+      sq += dot4(r.u[k], r.u[k]) + dot4(r.p[k], r.p[k]) + dot4(r.n[k], r.n[k]);
+    }
+    l2_acc += sq;  // invalid triplets contribute exact zeros
+    s1 = orx_group_sum<G>(s1);
+    s2 = orx_group_sum<G>(s2);
+    float lt, g;
+    pair_score<KIND>(s1, s2, r.bp, r.bn, a, &lt, &g);
+    const bool v = r.fl & 1;
+    if (!v) { lt = 0.f; g = 0.f; }
+    if (gl == 0) loss_acc += lt;
+    // bias gradient of the positive item: BPR +g, UCML -a  (negative item gets the opposite sign)
+    const float gbias = (KIND == ORX_PAIR_BPR) ? g : -g;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      const float val = __shfl_sync(ORX_FULL, gbias, q * G);
+      if (lane == j + q) g_own = val;
+    }
+    if (v) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int off = (k * G + gl) * 4;
+        float4 gu, gp, gn;
+        pair_row_grads<KIND>(g, a.c_l2, r.u[k], r.p[k], r.n[k], &gu, &gp, &gn);
+        if (!STAGE_ONLY && (r.fl & 2)) {
+          const int64_t o = (int64_t)r.uu * D + off;
+          __stcg(reinterpret_cast<float4*>(a.U + o), orx_apply4<OPT>(r.u[k], gu, r.us0[k], r.us1[k], a.opt));
+          if (S0) __stcg(reinterpret_cast<float4*>(a.Us0 + o), r.us0[k]);
+          if (S1) __stcg(reinterpret_cast<float4*>(a.Us1 + o), r.us1[k]);
+        } else {
+          orx_red4(a.gu + (int64_t)r.du * D + off, gu);
+        }
+        if (!STAGE_ONLY && (r.fl & 4)) {
+          const int64_t o = (int64_t)r.pp * D + off;
+          __stcg(reinterpret_cast<float4*>(a.I + o), orx_apply4<OPT>(r.p[k], gp, r.ps0[k], r.ps1[k], a.opt));
+          if (S0) __stcg(reinterpret_cast<float4*>(a.Is0 + o), r.ps0[k]);
+          if (S1) __stcg(reinterpret_cast<float4*>(a.Is1 + o), r.ps1[k]);
+        } else {
+          orx_red4(a.gi + (int64_t)r.dp * D + off, gp);
+        }
+        if (!STAGE_ONLY && (r.fl & 8)) {
+          const int64_t o = (int64_t)r.nn * D + off;
+          __stcg(reinterpret_cast<float4*>(a.I + o), orx_apply4<OPT>(r.n[k], gn, r.ns0[k], r.ns1[k], a.opt));
+          if (S0) __stcg(reinterpret_cast<float4*>(a.Is0 + o), r.ns0[k]);
+          if (S1) __stcg(reinterpret_cast<float4*>(a.Is1 + o), r.ns1[k]);
+        } else {
+          orx_red4(a.gi + (int64_t)r.dn * D + off, gn);
+        }
+      }
+    }
+  };
+
+  if (PIPE) {
+    Regs ra, rb;
+    load(0, ra);
+#pragma unroll 1
+    for (int j = 0; j < CH; j += 2 * TPW) {
+      const bool has_b = (j + TPW < CH);
+      if (has_b) load(j + TPW, rb);
+      process(j, ra);
+      if (j + 2 * TPW < CH) load(j + 2 * TPW, ra);
+      if (has_b) process(j + TPW, rb);
+    }
+  } else {
+    Regs ra;
+#pragma unroll 1
+    for (int j = 0; j < CH; j += TPW) {
+      load(j, ra);
+      process(j, ra);
+    }
+  }
+
+  // ---- item_bias: lane-parallel, one lane per triplet of the chunk
+  if (flags & 1) {
+    if (flags & 4) {
+      __stcg(a.Bv + p_id, orx_apply<OPT>(bp, g_own, bps0, bps1, a.opt));
+      if (S0) __stcg(a.Bs0 + p_id, bps0);
+      if (S1) __stcg(a.Bs1 + p_id, bps1);
+    } else {
+      atomicAdd(a.gb + dp, g_own);
+    }
+    if (flags & 8) {
+      __stcg(a.Bv + n_id, orx_apply<OPT>(bn, -g_own, bns0, bns1, a.opt));
+      if (S0) __stcg(a.Bs0 + n_id, bns0);
+      if (S1) __stcg(a.Bs1 + n_id, bns1);
+    } else {
+      atomicAdd(a.gb + dn, -g_own);
+    }
+    if (a.g_out) a.g_out[t] = (KIND == ORX_PAIR_BPR) ? g_own : -g_own;
+  } else if (a.g_out && lane < CH && t < a.B) {
+    a.g_out[t] = 0.f;
+  }
+
+  loss_acc = orx_group_sum<32>(loss_acc);
+  l2_acc = orx_group_sum<32>(l2_acc);
+  if (lane == 0) {
+    a.partials[2 * warp] = loss_acc;
+    a.partials[2 * warp + 1] = l2_acc;
+  }
+}
+
+// Any dim (e.g. the example's D=50): one triplet per warp-iteration, lanes stride the row.
+template <int KIND, int OPT>
+__global__ void __launch_bounds__(256) k_pair_step_generic(const PairArgs a) {
+  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool STAGE_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
+  constexpr int CH = 8;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int D = a.D;
+  float loss_acc = 0.f, l2_acc = 0.f;
+  for (int j = 0; j < CH; ++j) {
+    const int t = warp * CH + j;
+    if (t >= a.B) break;
+    const int uu = a.uid[t], pp = a.pid[t], nn = a.nid[t];
+    const bool ok = uu >= 0 && uu < a.rowsU && pp >= 0 && pp < a.rowsI && nn >= 0 && nn < a.rowsI;
+    if (!ok) {
+      if (a.g_out && lane == 0) a.g_out[t] = 0.f;
+      continue;
+    }
+    int du, dp, dn;
+    const uint32_t cu = orx_hash_find(a.hu, uu, &du);
+    const uint32_t cp = orx_hash_find(a.hi, pp, &dp);
+    const uint32_t cn = orx_hash_find(a.hi, nn, &dn);
+    const bool fu = !STAGE_ONLY && cu == 1u, fp = !STAGE_ONLY && cp == 1u, fn = !STAGE_ONLY && cn == 1u;
+    float* ur = a.U + (int64_t)uu * D;
+    float* pr = a.I + (int64_t)pp * D;
+    float* nr = a.I + (int64_t)nn * D;
+    float s1 = 0.f, s2 = 0.f, sq = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float u = ur[d], p = pr[d], n = nr[d];
+      if (KIND == ORX_PAIR_BPR) {
+        s1 += u * p;
+        s2 += u * n;
+      } else {
+        s1 += (u - p) * (u - p);
+        s2 += (u - n) * (u - n);
+      }
+      sq += u * u + p * p + n * n;
+    }
+    l2_acc += sq;
+    s1 = orx_group_sum<32>(s1);
+    s2 = orx_group_sum<32>(s2);
+    const float bp = a.Bv[pp], bn = a.Bv[nn];
+    float lt, g;
+    pair_score<KIND>(s1, s2, bp, bn, a, &lt, &g);
+    if (lane == 0) loss_acc += lt;
+    const float t2 = 2.f * g, c2 = a.c_l2;
+    for (int d = lane; d < D; d += 32) {
+      const float u = ur[d], p = pr[d], n = nr[d];
+      float gu, gp, gn;
+      if (KIND == ORX_PAIR_BPR) {
+        gu = g * (p - n) + c2 * u;
+        gp = g * u + c2 * p;
+        gn = -g * u + c2 * n;
+      } else {
+        gu = t2 * (n - p) + c2 * u;
+        gp = t2 * (p - u) + c2 * p;
+        gn = t2 * (u - n) + c2 * n;
+      }
+      float s0v = 0.f, s1v = 0.f;
+      if (fu) {
+        const int64_t o = (int64_t)uu * D + d;
+        if (S0) s0v = a.Us0[o];
+        if (S1) s1v = a.Us1[o];
+        ur[d] = orx_apply<OPT>(u, gu, s0v, s1v, a.opt);
+        if (S0) a.Us0[o] = s0v;
+        if (S1) a.Us1[o] = s1v;
+      } else {
+        atomicAdd(a.gu + (int64_t)du * D + d, gu);
+      }
+      if (fp) {
+        const int64_t o = (int64_t)pp * D + d;
+        if (S0) s0v = a.Is0[o];
+        if (S1) s1v = a.Is1[o];
+        pr[d] = orx_apply<OPT>(p, gp, s0v, s1v, a.opt);
+        if (S0) a.Is0[o] = s0v;
+        if (S1) a.Is1[o] = s1v;
+      } else {
+        atomicAdd(a.gi + (int64_t)dp * D + d, gp);
+      }
+      if (fn) {
+        const int64_t o = (int64_t)nn * D + d;
+        if (S0) s0v = a.Is0[o];
+        if (S1) s1v = a.Is1[o];
+        nr[d] = orx_apply<OPT>(n, gn, s0v, s1v, a.opt);
+        if (S0) a.Is0[o] = s0v;
+        if (S1) a.Is1[o] = s1v;
+      } else {
+        atomicAdd(a.gi + (int64_t)dn * D + d, gn);
+      }
+    }
+    if (lane == 0) {
+      const float gbias = (KIND == ORX_PAIR_BPR) ? g : -g;
+      float s0v = 0.f, s1v = 0.f;
+      if (fp) {
+        if (S0) s0v = a.Bs0[pp];
+        if (S1) s1v = a.Bs1[pp];
+        a.Bv[pp] = orx_apply<OPT>(bp, gbias, s0v, s1v, a.opt);
+        if (S0) a.Bs0[pp] = s0v;
+        if (S1) a.Bs1[pp] = s1v;
+      } else {
+        atomicAdd(a.gb + dp, gbias);
+      }
+      if (fn) {
+        if (S0) s0v = a.Bs0[nn];
+        if (S1) s1v = a.Bs1[nn];
+        a.Bv[nn] = orx_apply<OPT>(bn, -gbias, s0v, s1v, a.opt);
+        if (S0) a.Bs0[nn] = s0v;
+        if (S1) a.Bs1[nn] = s1v;
+      } else {
+        atomicAdd(a.gb + dn, -gbias);
+      }
+      if (a.g_out) a.g_out[t] = g;
+    }
+  }
+  loss_acc = orx_group_sum<32>(loss_acc);
+  l2_acc = orx_group_sum<32>(l2_acc);
+  if (lane == 0) {
+    a.partials[2 * warp] = loss_acc;
+    a.partials[2 * warp + 1] = l2_acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// ADAM_DENSE sweep: Keras-2.0 Adam on IndexedSlices touches EVERY row ("K12").
+// One warp per table row; the row's summed gradient comes from the staging buffer via the hash.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_adam_sweep(float* var, float* m, float* v, int64_t rows, int D, OrxHash h,
+                                                    const float* gstage, OrxOptDev o) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += nw) {
+    int d = -1;
+    uint32_t c = 0;
+    if (lane == 0) c = orx_hash_find(h, (int32_t)r, &d);
+    c = __shfl_sync(ORX_FULL, c, 0);
+    d = __shfl_sync(ORX_FULL, d, 0);
+    for (int e = lane; e < D; e += 32) {
+      const int64_t off = r * D + e;
+      const float g = c ? gstage[(int64_t)d * D + e] : 0.f;
+      const float mm = o.beta1 * m[off] + (1.f - o.beta1) * g;
+      const float vv = o.beta2 * v[off] + (1.f - o.beta2) * g * g;
+      m[off] = mm;
+      v[off] = vv;
+      var[off] = var[off] - o.lr * mm / (sqrtf(vv) + o.eps);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tail: staged rows -> optimizer (once per unique row), zero staging, clear hash, reduce loss
+// ---------------------------------------------------------------------------------------
+
+template <int OPT>
+__global__ void __launch_bounds__(256) k_sparse_tail(const TailArgs a) {
+  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool ZERO_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nu = a.counters[0], ni = a.counters[1], nbad = a.counters[3];
+  const int D = a.D;
+  for (int r = gwarp; r < nu + ni; r += nwarps) {
+    const bool is_u = r < nu;
+    const int d = is_u ? r : r - nu;
+    const int id = is_u ? a.hu.did[d] : a.hi.did[d];
+    float* G = (is_u ? a.gu : a.gi) + (int64_t)d * D;
+    float* W = (is_u ? a.U : a.I) + (int64_t)id * D;
+    float* P0 = (is_u ? a.Us0 : a.Is0) + (int64_t)id * D;
+    float* P1 = (is_u ? a.Us1 : a.Is1) + (int64_t)id * D;
+    for (int e = lane; e < D; e += 32) {
+      if (!ZERO_ONLY) {
+        float s0v = S0 ? P0[e] : 0.f, s1v = S1 ? P1[e] : 0.f;
+        W[e] = orx_apply<OPT>(W[e], G[e], s0v, s1v, a.opt);
+        if (S0) P0[e] = s0v;
+        if (S1) P1[e] = s1v;
+      }
+      G[e] = 0.f;
+    }
+    if (!is_u && lane == 0) {
+      if (!ZERO_ONLY) {
+        float s0v = S0 ? a.Bs0[id] : 0.f, s1v = S1 ? a.Bs1[id] : 0.f;
+        a.Bv[id] = orx_apply<OPT>(a.Bv[id], a.gb[d], s0v, s1v, a.opt);
+        if (S0) a.Bs0[id] = s0v;
+        if (S1) a.Bs1[id] = s1v;
+      }
+      a.gb[d] = 0.f;
+    }
+  }
+  // clear both hash tables for the next step
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (uint32_t i = tid; i <= a.hu.mask; i += nth) a.hu.slots[i] = 0ull;
+  for (uint32_t i = tid; i <= a.hi.mask; i += nth) a.hi.slots[i] = 0ull;
+
+  __shared__ double sh[2][256];
+  __shared__ bool last;
+  if (blockIdx.x == 0) {
+    // deterministic loss reduction (fixed order, double accumulation)
+    double l = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < a.n_partials; i += blockDim.x) {
+      l += (double)a.partials[2 * i];
+      q += (double)a.partials[2 * i + 1];
+    }
+    if (a.W)  // GMF: l2_loss also holds 0.5*sum(w^2) of the PRE-step weight (gmf.py:31-32)
+      for (int e = threadIdx.x; e < D; e += blockDim.x) q += (double)a.W[e] * (double)a.W[e];
+    sh[0][threadIdx.x] = l;
+    sh[1][threadIdx.x] = q;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+        sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      a.out4[0] = (float)(sh[0][0] * (double)a.loss_scale);
+      a.out4[1] = (float)(0.5 * sh[1][0]);
+      a.out4[2] = (float)nbad;
+      a.out4[3] = (float)(nu + ni);
+    }
+    // GMF dense weight: grad = gw + c_l2*w  (gmf.py:31-32), Keras dense apply
+    if (a.W) {
+      for (int e = threadIdx.x; e < D; e += blockDim.x) {
+        const float g = a.gw[e] + a.c_l2 * a.W[e];
+        if (ZERO_ONLY) {  // ADAM_DENSE: dense Adam
+          const float mm = a.opt.beta1 * a.Ws0[e] + (1.f - a.opt.beta1) * g;
+          const float vv = a.opt.beta2 * a.Ws1[e] + (1.f - a.opt.beta2) * g * g;
+          a.Ws0[e] = mm;
+          a.Ws1[e] = vv;
+          a.W[e] = a.W[e] - a.opt.lr * mm / (sqrtf(vv) + a.opt.eps);
+        } else {
+          float s0v = S0 ? a.Ws0[e] : 0.f, s1v = S1 ? a.Ws1[e] : 0.f;
+          a.W[e] = orx_apply<OPT>(a.W[e], g, s0v, s1v, a.opt);
+          if (S0) a.Ws0[e] = s0v;
+          if (S1) a.Ws1[e] = s1v;
+        }
+        a.gw[e] = 0.f;
+      }
+    }
+  }
+  // last block to finish resets the counters (every block has read them by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int tk = atomicAdd(a.counters + 2, 1);
+    last = (tk == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 4) a.counters[threadIdx.x] = 0;
+}
+
+int orx_launch_tail(orx_ctx* c, const TailArgs& ta, int opt_kind, cudaStream_t st) {
+  const int grid = c->num_sms * 2;
+  switch (opt_kind) {
+    case ORX_OPT_SGD: k_sparse_tail<ORX_OPT_SGD><<<grid, 256, 0, st>>>(ta); break;
+    case ORX_OPT_ADAGRAD: k_sparse_tail<ORX_OPT_ADAGRAD><<<grid, 256, 0, st>>>(ta); break;
+    case ORX_OPT_ADAM_LAZY: k_sparse_tail<ORX_OPT_ADAM_LAZY><<<grid, 256, 0, st>>>(ta); break;
+    default: k_sparse_tail<ORX_OPT_ADAM_DENSE><<<grid, 256, 0, st>>>(ta); break;
+  }
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t rows, int D, const OrxHash& h,
+                          const float* gstage, const OrxOptDev& o, cudaStream_t st) {
+  int64_t blocks = (rows + 7) / 8;
+  const int64_t cap = (int64_t)c->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_adam_sweep<<<(int)blocks, 256, 0, st>>>(var, m, v, rows, D, h, gstage, o);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------------------
+template <int KIND, int OPT>
+static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaStream_t st, int* n_partials) {
+  const int B = pa.B;
+  auto go = [&](auto kern, int ch) {
+    const int nw = (B + ch - 1) / ch;
+    const int blocks = (nw + 7) / 8;
+    *n_partials = blocks * 8;
+    kern<<<blocks, 256, 0, st>>>(pa);
+  };
+  (void)n_warps_hint;
+  switch (pa.D) {
+    case 32: go(k_pair_step<KIND, OPT, 32, 8>, 8); break;
+    case 64: go(k_pair_step<KIND, OPT, 64, 8>, 8); break;
+    case 128: go(k_pair_step<KIND, OPT, 128, 8>, 8); break;
+    case 256: go(k_pair_step<KIND, OPT, 256, 8>, 8); break;
+    default: go(k_pair_step_generic<KIND, OPT>, 8); break;
+  }
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+template <int KIND>
+static int launch_pair_step_kind(const PairArgs& pa, int opt_kind, cudaStream_t st, int* n_partials) {
+  switch (opt_kind) {
+    case ORX_OPT_SGD: return launch_pair_step_kind_opt<KIND, ORX_OPT_SGD>(pa, 0, st, n_partials);
+    case ORX_OPT_ADAGRAD: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAGRAD>(pa, 0, st, n_partials);
+    case ORX_OPT_ADAM_LAZY: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAM_LAZY>(pa, 0, st, n_partials);
+    case ORX_OPT_ADAM_DENSE: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAM_DENSE>(pa, 0, st, n_partials);
+  }
+  orx_set_error("unknown optimizer kind %d", opt_kind);
+  return ORX_ERR_INVALID;
+}
+
+static int check_tables(const orx_table_t* user, const orx_table_t* item, const orx_table_t* bias, int opt_kind) {
+  ORX_REQUIRE(user && item && bias, "null table");
+  ORX_REQUIRE(user->var && item->var && bias->var, "null table storage");
+  ORX_REQUIRE(user->dim == item->dim && user->dim > 0, "user/item dims must match and be positive");
+  ORX_REQUIRE(bias->dim == 1 && bias->rows == item->rows, "item_bias must be [item.rows, 1]");
+  ORX_REQUIRE(user->rows > 0 && item->rows > 0 && user->rows <= 0x7fffffffLL && item->rows <= 0x7fffffffLL,
+              "row counts must fit int32 ids");
+  if (opt_kind != ORX_OPT_SGD) ORX_REQUIRE(user->s0 && item->s0 && bias->s0, "optimizer slot s0 missing");
+  if (opt_kind == ORX_OPT_ADAM_LAZY || opt_kind == ORX_OPT_ADAM_DENSE)
+    ORX_REQUIRE(user->s1 && item->s1 && bias->s1, "optimizer slot s1 missing");
+  return ORX_OK;
+}
+
+static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, const orx_table_t* item,
+                              const orx_table_t* bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
+                              int B, float margin, float c_loss, float c_l2, const orx_opt_t* opt, float* out4,
+                              cudaStream_t st) {
+  ORX_REQUIRE(kind == ORX_PAIR_BPR || kind == ORX_PAIR_UCML, "unknown pairwise kind");
+  ORX_REQUIRE(opt != nullptr && out4 != nullptr, "null opt/out");
+  ORX_REQUIRE(opt->kind >= ORX_OPT_SGD && opt->kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
+  ORX_REQUIRE(B > 0 && uid && pid && nid, "empty batch or null ids");
+  int rc = check_tables(user, item, bias, opt->kind);
+  if (rc) return rc;
+  const int D = user->dim;
+  if ((rc = orx_ensure_workspace(c, B, D, opt->kind == ORX_OPT_ADAM_DENSE))) return rc;
+  const bool dense = opt->kind == ORX_OPT_ADAM_DENSE;
+  if ((rc = orx_launch_index_build(c, uid, user->rows, B, pid, nid, item->rows, B, dense, st))) return rc;
+
+  PairArgs pa;
+  pa.U = user->var; pa.Us0 = user->s0; pa.Us1 = user->s1;
+  pa.I = item->var; pa.Is0 = item->s0; pa.Is1 = item->s1;
+  pa.Bv = bias->var; pa.Bs0 = bias->s0; pa.Bs1 = bias->s1;
+  pa.rowsU = user->rows; pa.rowsI = item->rows; pa.D = D;
+  pa.uid = uid; pa.pid = pid; pa.nid = nid; pa.B = B;
+  pa.margin = margin; pa.c_loss = c_loss; pa.c_l2 = c_l2; pa.inv_B = 1.0f / (float)B;
+  pa.opt = orx_opt_to_dev(opt);
+  pa.hu = c->hu; pa.hi = c->hi; pa.gu = c->gu; pa.gi = c->gi; pa.gb = c->gb;
+  pa.partials = c->partials; pa.g_out = nullptr;
+  if ((rc = orx_ensure_partials(c, (B + 7) / 8 + 8, st))) return rc;
+  pa.partials = c->partials;
+  int n_partials = 0;
+  rc = (kind == ORX_PAIR_BPR) ? launch_pair_step_kind<ORX_PAIR_BPR>(pa, opt->kind, st, &n_partials)
+                              : launch_pair_step_kind<ORX_PAIR_UCML>(pa, opt->kind, st, &n_partials);
+  if (rc) return rc;
+  if (dense) {
+    if ((rc = orx_launch_adam_sweep(c, user->var, user->s0, user->s1, user->rows, D, c->hu, c->gu, pa.opt, st))) return rc;
+    if ((rc = orx_launch_adam_sweep(c, item->var, item->s0, item->s1, item->rows, D, c->hi, c->gi, pa.opt, st))) return rc;
+    if ((rc = orx_launch_adam_sweep(c, bias->var, bias->s0, bias->s1, bias->rows, 1, c->hi, c->gb, pa.opt, st))) return rc;
+  }
+  TailArgs ta;
+  ta.U = user->var; ta.Us0 = user->s0; ta.Us1 = user->s1;
+  ta.I = item->var; ta.Is0 = item->s0; ta.Is1 = item->s1;
+  ta.Bv = bias->var; ta.Bs0 = bias->s0; ta.Bs1 = bias->s1;
+  ta.D = D; ta.opt = pa.opt; ta.hu = c->hu; ta.hi = c->hi;
+  ta.gu = c->gu; ta.gi = c->gi; ta.gb = c->gb;
+  ta.partials = c->partials; ta.n_partials = n_partials;
+  ta.loss_scale = (kind == ORX_PAIR_BPR) ? pa.inv_B : 1.0f;
+  ta.counters = c->counters; ta.out4 = out4;
+  ta.W = ta.Ws0 = ta.Ws1 = ta.gw = nullptr; ta.c_l2 = c_l2;
+  return orx_launch_tail(c, ta, opt->kind, st);
+}
+
+extern "C" int orx_pairwise_step(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                                 const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid,
+                                 const int32_t* nid, int32_t B, float margin, float c_loss, float c_l2,
+                                 const orx_opt_t* opt, float* out4, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr, "null handle");
+  ORX_CUDA(cudaSetDevice(h->device));
+  return pairwise_step_impl(h, kind, user, item, item_bias, uid, pid, nid, B, margin, c_loss, c_l2, opt, out4,
+                            (cudaStream_t)s);
+}
+
+extern "C" int orx_pairwise_step_host(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                                      const orx_table_t* item_bias, const int32_t* uid_host, const int32_t* pid_host,
+                                      const int32_t* nid_host, int32_t B, float margin, float c_loss, float c_l2,
+                                      const orx_opt_t* opt, float* out4_host, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr, "null handle");
+  ORX_REQUIRE(B > 0 && uid_host && pid_host && nid_host && out4_host, "empty batch or null host buffers");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)s;
+  int rc = orx_ensure_stage(h, 3 * (int64_t)B);
+  if (rc) return rc;
+  const uint32_t f = (h->stage_flip++) & 1u;
+  int32_t* ids = h->ids_stage[f];
+  ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+  ORX_CUDA(cudaMemcpyAsync(ids + B, pid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+  ORX_CUDA(cudaMemcpyAsync(ids + 2 * (int64_t)B, nid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+  rc = pairwise_step_impl(h, kind, user, item, item_bias, ids, ids + B, ids + 2 * (int64_t)B, B, margin, c_loss, c_l2,
+                          opt, h->out_stage[f], st);
+  if (rc) return rc;
+  ORX_CUDA(cudaMemcpyAsync(out4_host, h->out_stage[f], sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
+  return ORX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// forward only / explicit gradients (un-fused; parity tests and the lazy-handle fallback)
+// ---------------------------------------------------------------------------------------
+struct PairGradArgs {
+  const float *U, *I, *Bv;
+  int64_t rowsU, rowsI;
+  int D;
+  const int32_t *uid, *pid, *nid;
+  int B;
+  float margin, c_loss, c_l2, inv_B;
+  float *d_user, *d_pos, *d_neg, *d_bp, *d_bn, *g_out;
+  float* partials;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_pair_fwd_grad(const PairGradArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int D = a.D;
+  float loss_acc = 0.f, l2_acc = 0.f;
+  PairArgs sa;  // only the scalar fields pair_score reads
+  sa.margin = a.margin;
+  sa.c_loss = a.c_loss;
+  sa.inv_B = a.inv_B;
+  for (int j = 0; j < 8; ++j) {
+    const int t = warp * 8 + j;
+    if (t >= a.B) break;
+    const int uu = a.uid[t], pp = a.pid[t], nn = a.nid[t];
+    const bool ok = uu >= 0 && uu < a.rowsU && pp >= 0 && pp < a.rowsI && nn >= 0 && nn < a.rowsI;
+    float s1 = 0.f, s2 = 0.f, sq = 0.f, bp = 0.f, bn = 0.f, lt = 0.f, g = 0.f;
+    const float* ur = a.U + (int64_t)uu * D;
+    const float* pr = a.I + (int64_t)pp * D;
+    const float* nr = a.I + (int64_t)nn * D;
+    if (ok) {
+      for (int d = lane; d < D; d += 32) {
+        const float u = ur[d], p = pr[d], n = nr[d];
+        if (KIND == ORX_PAIR_BPR) {
+          s1 += u * p;
+          s2 += u * n;
+        } else {
+          s1 += (u - p) * (u - p);
+          s2 += (u - n) * (u - n);
+        }
+        sq += u * u + p * p + n * n;
+      }
+      bp = a.Bv[pp];
+      bn = a.Bv[nn];
+    }
+    l2_acc += sq;
+    s1 = orx_group_sum<32>(s1);
+    s2 = orx_group_sum<32>(s2);
+    if (ok) pair_score<KIND>(s1, s2, bp, bn, sa, &lt, &g);
+    if (lane == 0) loss_acc += lt;
+    const float t2 = 2.f * g, c2 = a.c_l2;
+    if (a.d_user || a.d_pos || a.d_neg) {
+      for (int d = lane; d < D; d += 32) {
+        float gu = 0.f, gp = 0.f, gn = 0.f;
+        if (ok) {
+          const float u = ur[d], p = pr[d], n = nr[d];
+          if (KIND == ORX_PAIR_BPR) {
+            gu = g * (p - n) + c2 * u;
+            gp = g * u + c2 * p;
+            gn = -g * u + c2 * n;
+          } else {
+            gu = t2 * (n - p) + c2 * u;
+            gp = t2 * (p - u) + c2 * p;
+            gn = t2 * (u - n) + c2 * n;
+          }
+        }
+        const int64_t o = (int64_t)t * D + d;
+        if (a.d_user) a.d_user[o] = gu;
+        if (a.d_pos) a.d_pos[o] = gp;
+        if (a.d_neg) a.d_neg[o] = gn;
+      }
+    }
+    if (lane == 0) {
+      const float gbias = (KIND == ORX_PAIR_BPR) ? g : -g;
+      if (a.d_bp) a.d_bp[t] = gbias;
+      if (a.d_bn) a.d_bn[t] = -gbias;
+      if (a.g_out) a.g_out[t] = g;
+    }
+  }
+  loss_acc = orx_group_sum<32>(loss_acc);
+  l2_acc = orx_group_sum<32>(l2_acc);
+  if (lane == 0) {
+    a.partials[2 * warp] = loss_acc;
+    a.partials[2 * warp + 1] = l2_acc;
+  }
+}
+
+__global__ void k_reduce_partials(const float* partials, int n, float loss_scale, float* out4) {
+  __shared__ double sh[2][256];
+  double l = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    l += (double)partials[2 * i];
+    q += (double)partials[2 * i + 1];
+  }
+  sh[0][threadIdx.x] = l;
+  sh[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out4[0] = (float)(sh[0][0] * (double)loss_scale);
+    out4[1] = (float)(0.5 * sh[1][0]);
+    out4[2] = 0.f;
+    out4[3] = 0.f;
+  }
+}
+
+int orx_launch_reduce_partials(const float* partials, int n, float loss_scale, float* out4, cudaStream_t st) {
+  k_reduce_partials<<<1, 256, 0, st>>>(partials, n, loss_scale, out4);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+int orx_ensure_partials(orx_ctx* c, int need, cudaStream_t st) {
+  if (need <= c->cap_partials) return ORX_OK;
+  ORX_CUDA(cudaStreamSynchronize(st));
+  cudaFree(c->partials);
+  c->partials = nullptr;
+  c->cap_partials = need * 2;
+  ORX_CUDA(cudaMalloc(&c->partials, sizeof(float) * 2 * (size_t)c->cap_partials));
+  return ORX_OK;
+}
+
+static int pair_fwd_grad(orx_ctx* c, int kind, const orx_table_t* user, const orx_table_t* item,
+                         const orx_table_t* bias, const int32_t* uid, const int32_t* pid, const int32_t* nid, int B,
+                         float margin, float c_loss, float c_l2, float* d_user, float* d_pos, float* d_neg,
+                         float* d_bp, float* d_bn, float* g_out, float* out4, cudaStream_t st) {
+  ORX_REQUIRE(kind == ORX_PAIR_BPR || kind == ORX_PAIR_UCML, "unknown pairwise kind");
+  ORX_REQUIRE(B > 0 && uid && pid && nid, "empty batch or null ids");
+  int rc = check_tables(user, item, bias, ORX_OPT_SGD);
+  if (rc) return rc;
+  const int nw = (B + 7) / 8, blocks = (nw + 7) / 8;
+  if ((rc = orx_ensure_partials(c, blocks * 8, st))) return rc;
+  PairGradArgs a;
+  a.U = user->var; a.I = item->var; a.Bv = bias->var;
+  a.rowsU = user->rows; a.rowsI = item->rows; a.D = user->dim;
+  a.uid = uid; a.pid = pid; a.nid = nid; a.B = B;
+  a.margin = margin; a.c_loss = c_loss; a.c_l2 = c_l2; a.inv_B = 1.0f / (float)B;
+  a.d_user = d_user; a.d_pos = d_pos; a.d_neg = d_neg; a.d_bp = d_bp; a.d_bn = d_bn; a.g_out = g_out;
+  a.partials = c->partials;
+  if (kind == ORX_PAIR_BPR) k_pair_fwd_grad<ORX_PAIR_BPR><<<blocks, 256, 0, st>>>(a);
+  else k_pair_fwd_grad<ORX_PAIR_UCML><<<blocks, 256, 0, st>>>(a);
+  ORX_LAUNCH_CHECK();
+  if (out4) {
+    return orx_launch_reduce_partials(c->partials, blocks * 8, kind == ORX_PAIR_BPR ? a.inv_B : 1.f, out4, st);
+  }
+  return ORX_OK;
+}
+
+extern "C" int orx_pairwise_fwd(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                                const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid,
+                                const int32_t* nid, int32_t B, float margin, float* out4, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && out4 != nullptr, "null handle/out");
+  ORX_CUDA(cudaSetDevice(h->device));
+  return pair_fwd_grad(h, kind, user, item, item_bias, uid, pid, nid, B, margin, 1.f, 1.f, nullptr, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, out4, (cudaStream_t)s);
+}
+
+extern "C" int orx_pairwise_grad(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
+                                 const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid,
+                                 const int32_t* nid, int32_t B, float margin, float c_loss, float c_l2, float* d_user,
+                                 float* d_pos, float* d_neg, float* d_bp, float* d_bn, float* g_out, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr, "null handle");
+  ORX_CUDA(cudaSetDevice(h->device));
+  return pair_fwd_grad(h, kind, user, item, item_bias, uid, pid, nid, B, margin, c_loss, c_l2, d_user, d_pos, d_neg,
+                       d_bp, d_bn, g_out, nullptr, (cudaStream_t)s);
+}

@@ -1,0 +1,177 @@
+"""Thin torch-tensor front of the C-ABI: torch owns device memory and streams (plumbing),
+liborx does all the arithmetic.  Every function enqueues on torch's current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ORX_OPT_ADAGRAD, ORX_OPT_ADAM_DENSE, ORX_OPT_ADAM_LAZY, ORX_OPT_SGD, ORX_PAIR_BPR,
+                   ORX_PAIR_UCML, ORX_POINT_GMF, ORX_POINT_WRMF, ORX_SCORE_DOT, ORX_SCORE_NEG_SQDIST, OrxOpt,
+                   OrxTable)
+
+__all__ = ["Engine", "engine", "table", "opt", "ORX_PAIR_BPR", "ORX_PAIR_UCML", "ORX_POINT_GMF", "ORX_POINT_WRMF",
+           "ORX_OPT_SGD", "ORX_OPT_ADAGRAD", "ORX_OPT_ADAM_LAZY", "ORX_OPT_ADAM_DENSE", "ORX_SCORE_DOT",
+           "ORX_SCORE_NEG_SQDIST"]
+
+_engines = {}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32(t, name):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError(f"{name}: expected a contiguous float32 CUDA tensor")
+    return t
+
+
+def ids32(t):
+    """int32 contiguous CUDA ids (Keras Embedding casts other integer dtypes to int32)."""
+    if not t.is_cuda:
+        raise ValueError("ids must live on the CUDA device")
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous().reshape(-1)
+
+
+def table(var, s0=None, s1=None):
+    """orx_table_t for a [rows, dim] variable and its optimizer slots."""
+    _f32(var, "var"), _f32(s0, "s0"), _f32(s1, "s1")
+    rows, dim = (var.shape[0], var.shape[1]) if var.dim() == 2 else (1, var.numel())
+    return OrxTable(var.data_ptr(), s0.data_ptr() if s0 is not None else None,
+                    s1.data_ptr() if s1 is not None else None, rows, dim)
+
+
+def opt(kind, lr, eps=1e-7, beta1=0.9, beta2=0.999, step=1):
+    return OrxOpt(kind, lr, eps, beta1, beta2, step)
+
+
+class Engine:
+    """One liborx context (workspace) per CUDA device."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lib = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(self.lib.orx_create(index, C.byref(h)), "orx_create")
+        self.h = h
+        self.device = torch.device("cuda", index)
+
+    def close(self):
+        if self.h:
+            self.lib.orx_destroy(self.h)
+            self.h = None
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- LatentFactor ------------------------------------------------------------------
+    def fill_uniform(self, dst, lo, hi, seed):
+        _lib.check(self.lib.orx_fill_uniform(self.h, _ptr(_f32(dst, "dst")), dst.numel(), lo, hi, seed, self.stream()))
+
+    def gather(self, tab, ids, n_bad=None):
+        is64 = ids.dtype == torch.int64
+        if not is64:
+            ids = ids32(ids)
+        ids = ids.contiguous().reshape(-1)
+        out = torch.empty((ids.numel(), tab.shape[1]), dtype=torch.float32, device=tab.device)
+        _lib.check(self.lib.orx_gather(self.h, _ptr(_f32(tab, "tab")), tab.shape[0], tab.shape[1], _ptr(ids),
+                                       1 if is64 else 0, ids.numel(), _ptr(out), _ptr(n_bad), self.stream()))
+        return out
+
+    def censor(self, tab, ids, min_norm=0.1):
+        ids = ids32(ids)
+        _lib.check(self.lib.orx_censor(self.h, _ptr(_f32(tab, "tab")), tab.shape[0], tab.shape[1], _ptr(ids),
+                                       ids.numel(), min_norm, self.stream()))
+
+    # ---- pairwise ----------------------------------------------------------------------
+    def pairwise_step(self, kind, user, item, bias, uid, pid, nid, o, out4, margin=0.5, c_loss=1.0, c_l2=1.0):
+        _lib.check(self.lib.orx_pairwise_step(self.h, kind, C.byref(user), C.byref(item), C.byref(bias), _ptr(uid),
+                                              _ptr(pid), _ptr(nid), uid.numel(), margin, c_loss, c_l2, C.byref(o),
+                                              _ptr(out4), self.stream()), "orx_pairwise_step")
+
+    def pairwise_step_host(self, kind, user, item, bias, uid_h, pid_h, nid_h, o, out4_h, margin=0.5, c_loss=1.0,
+                           c_l2=1.0):
+        """ids / out4 are (pinned) HOST tensors; copies ride the same stream as the kernels."""
+        _lib.check(self.lib.orx_pairwise_step_host(self.h, kind, C.byref(user), C.byref(item), C.byref(bias),
+                                                   _ptr(uid_h), _ptr(pid_h), _ptr(nid_h), uid_h.numel(), margin,
+                                                   c_loss, c_l2, C.byref(o), _ptr(out4_h), self.stream()),
+                   "orx_pairwise_step_host")
+
+    def pairwise_fwd(self, kind, user, item, bias, uid, pid, nid, out4, margin=0.5):
+        _lib.check(self.lib.orx_pairwise_fwd(self.h, kind, C.byref(user), C.byref(item), C.byref(bias), _ptr(uid),
+                                             _ptr(pid), _ptr(nid), uid.numel(), margin, _ptr(out4), self.stream()),
+                   "orx_pairwise_fwd")
+
+    def pairwise_grad(self, kind, user, item, bias, uid, pid, nid, margin=0.5, c_loss=1.0, c_l2=1.0, *, d_user=None,
+                      d_pos=None, d_neg=None, d_bp=None, d_bn=None, g_out=None):
+        _lib.check(self.lib.orx_pairwise_grad(self.h, kind, C.byref(user), C.byref(item), C.byref(bias), _ptr(uid),
+                                              _ptr(pid), _ptr(nid), uid.numel(), margin, c_loss, c_l2, _ptr(d_user),
+                                              _ptr(d_pos), _ptr(d_neg), _ptr(d_bp), _ptr(d_bn), _ptr(g_out),
+                                              self.stream()), "orx_pairwise_grad")
+
+    # ---- pointwise ---------------------------------------------------------------------
+    def pointwise_step(self, kind, user, item, bias, w, uid, iid, label, o, out4, a=1.0, b=1.0, use_sigmoid=False,
+                       c_loss=1.0, c_l2=1.0):
+        _lib.check(self.lib.orx_pointwise_step(self.h, kind, C.byref(user), C.byref(item), C.byref(bias),
+                                               C.byref(w) if w is not None else None, _ptr(uid), _ptr(iid),
+                                               _ptr(label), uid.numel(), a, b, int(use_sigmoid), c_loss, c_l2,
+                                               C.byref(o), _ptr(out4), self.stream()), "orx_pointwise_step")
+
+    def pointwise_fwd(self, kind, user, item, bias, w, uid, iid, label, out4, a=1.0, b=1.0, use_sigmoid=False):
+        _lib.check(self.lib.orx_pointwise_fwd(self.h, kind, C.byref(user), C.byref(item), C.byref(bias),
+                                              C.byref(w) if w is not None else None, _ptr(uid), _ptr(iid),
+                                              _ptr(label), uid.numel(), a, b, int(use_sigmoid), _ptr(out4),
+                                              self.stream()), "orx_pointwise_fwd")
+
+    def pointwise_grad(self, kind, user, item, bias, w, uid, iid, label, a=1.0, b=1.0, use_sigmoid=False, c_loss=1.0,
+                       c_l2=1.0, *, d_user=None, d_item=None, d_bias=None, d_w=None, g_out=None):
+        _lib.check(self.lib.orx_pointwise_grad(self.h, kind, C.byref(user), C.byref(item), C.byref(bias),
+                                               C.byref(w) if w is not None else None, _ptr(uid), _ptr(iid),
+                                               _ptr(label), uid.numel(), a, b, int(use_sigmoid), c_loss, c_l2,
+                                               _ptr(d_user), _ptr(d_item), _ptr(d_bias), _ptr(d_w), _ptr(g_out),
+                                               self.stream()), "orx_pointwise_grad")
+
+    # ---- dense / inference / metrics -----------------------------------------------------
+    def dense_apply(self, var, s0, s1, grad, o):
+        _lib.check(self.lib.orx_dense_apply(self.h, _ptr(_f32(var, "var")), _ptr(s0), _ptr(s1),
+                                            _ptr(_f32(grad, "grad")), var.numel(), C.byref(o), self.stream()),
+                   "orx_dense_apply")
+
+    def score_all(self, kind, user_tab, uid, item_tab, item_bias, scale=None):
+        uid = ids32(uid)
+        out = torch.empty((uid.numel(), item_tab.shape[0]), dtype=torch.float32, device=item_tab.device)
+        _lib.check(self.lib.orx_score_all(self.h, kind, _ptr(_f32(user_tab, "user_tab")), user_tab.shape[0], _ptr(uid),
+                                          uid.numel(), _ptr(scale), _ptr(_f32(item_tab, "item_tab")),
+                                          _ptr(item_bias), item_tab.shape[0], item_tab.shape[1], _ptr(out),
+                                          self.stream()), "orx_score_all")
+        return out
+
+    def rank_metrics(self, pred, pos, excl, at=(), want=("auc", "ndcg", "recall")):
+        pred = _f32(pred.contiguous(), "pred")
+        pos = pos.to(torch.uint8).contiguous()
+        excl = excl.to(torch.uint8).contiguous()
+        R, I = pred.shape
+        at_arr = (C.c_int32 * max(len(at), 1))(*[int(k) for k in at])
+        auc = torch.empty(R, dtype=torch.float32, device=pred.device) if "auc" in want else None
+        ndcg = torch.empty((R, len(at)), dtype=torch.float32, device=pred.device) if "ndcg" in want else None
+        rec = torch.empty((R, len(at)), dtype=torch.float32, device=pred.device) if "recall" in want else None
+        _lib.check(self.lib.orx_rank_metrics(self.h, _ptr(pred), _ptr(pos), _ptr(excl), R, I, at_arr, len(at),
+                                             _ptr(auc), _ptr(ndcg), _ptr(rec), self.stream()), "orx_rank_metrics")
+        return auc, ndcg, rec
+
+
+def engine(device=None) -> Engine:
+    """The per-device engine; raises (no CPU fallback) when CUDA is unavailable."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("openrec_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    e = _engines.get(idx)
+    if e is None:
+        e = _engines[idx] = Engine(idx)
+    return e

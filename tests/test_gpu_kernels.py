@@ -1,0 +1,355 @@
+"""GPU parity: every liborx entry point vs the oracle, through the C-ABI (ctypes).
+Bar: indices bit-exact (out-of-range / duplicate handling), loss / gradients / updated rows
+within 1e-5 (fp32) of the oracle evaluated in float64 on identical weights and ids."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import openrec_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ATOL = 1e-5
+OPTS = {"sgd": (0, 0.05), "adagrad": (1, 0.05), "adam_lazy": (2, 0.01), "adam_dense": (3, 0.01)}
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from openrec_b200 import native
+    return native.engine()
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype)
+
+
+def make_problem(rng, U, I, D, B, scale=0.05):
+    user = rng.uniform(-scale, scale, (U, D))
+    item = rng.uniform(-scale, scale, (I, D))
+    bias = rng.uniform(-scale, scale, (I, 1))
+    uid = rng.integers(0, U, B).astype(np.int32)
+    pid = rng.integers(0, I, B).astype(np.int32)
+    nid = rng.integers(0, I, B).astype(np.int32)
+    if B >= 4:
+        nid[1] = pid[1]   # same item as positive and negative of one triplet
+        uid[2] = uid[3]   # guaranteed duplicate user
+    return user, item, bias, uid, pid, nid
+
+
+def slots(opt_kind, *arrs):
+    """float64 oracle state + device tensors for the given optimizer."""
+    st, dv = {}, {}
+    for name, a in arrs:
+        if opt_kind == 0:
+            st[name], dv[name] = (None, None), (None, None)
+        elif opt_kind == 1:
+            s0 = np.full_like(a, 0.1)
+            st[name], dv[name] = (s0, None), (dev(s0), None)
+        else:
+            s0, s1 = np.abs(a) * 0.01, a * a * 0.02 + 1e-4   # non-trivial m, v
+            st[name], dv[name] = (s0.copy(), s1.copy()), (dev(s0), dev(s1))
+    return st, dv
+
+
+def close(t, ref, atol=ATOL, rtol=1e-5, what=""):
+    got = t.detach().cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(got, np.asarray(ref, dtype=np.float64).reshape(got.shape), atol=atol, rtol=rtol,
+                               err_msg=what)
+
+
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["bpr", "ucml"])
+def test_pairwise_golden_fwd_grad(eng, golden_dir, kind):
+    from openrec_b200 import native as N
+    g = dict(np.load(os.path.join(golden_dir, f"pairwise_{kind}.npz")))
+    tu, ti, tb = dev(g["user"]), dev(g["item"]), dev(g["bias"])
+    U, D = g["user"].shape
+    B = len(g["uid"])
+    uid, pid, nid = dev(g["uid"], torch.int32), dev(g["pid"], torch.int32), dev(g["nid"], torch.int32)
+    k = N.ORX_PAIR_BPR if kind == "bpr" else N.ORX_PAIR_UCML
+    out4 = torch.zeros(4, device="cuda")
+    eng.pairwise_fwd(k, N.table(tu), N.table(ti), N.table(tb), uid, pid, nid, out4, margin=0.5)
+    close(out4[0], g["loss"], what="loss")
+    close(out4[1], g["l2"], what="l2")
+    du, dp, dn = (torch.empty(B, D, device="cuda") for _ in range(3))
+    dbp, dbn = torch.empty(B, device="cuda"), torch.empty(B, device="cuda")
+    eng.pairwise_grad(k, N.table(tu), N.table(ti), N.table(tb), uid, pid, nid, 0.5, 1.0, 1.0, d_user=du, d_pos=dp,
+                      d_neg=dn, d_bp=dbp, d_bn=dbn)
+    dense_u = torch.zeros_like(tu).index_add_(0, uid.long(), du)
+    dense_i = torch.zeros_like(ti).index_add_(0, pid.long(), dp).index_add_(0, nid.long(), dn)
+    dense_b = torch.zeros(len(g["bias"]), device="cuda").index_add_(0, pid.long(), dbp).index_add_(0, nid.long(), dbn)
+    tol = 2e-4 if kind == "ucml" else ATOL   # the ucml fixture scales embeddings x8 (values ~O(10))
+    close(dense_u, g["g_user"], atol=tol, what="g_user")
+    close(dense_i, g["g_item"], atol=tol, what="g_item")
+    close(dense_b, g["g_bias"], atol=tol, what="g_bias")
+
+
+@pytest.mark.parametrize("kind", ["bpr", "ucml"])
+@pytest.mark.parametrize("optname", list(OPTS))
+@pytest.mark.parametrize("D,U,I,B", [(12, 37, 53, 96), (50, 300, 500, 257), (32, 64, 64, 200), (64, 2000, 3000, 1000),
+                                     (128, 5000, 9000, 4096), (256, 500, 700, 333)])
+def test_pairwise_step(eng, kind, optname, D, U, I, B):
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(hash((kind, optname, D)) % 2**31)
+    scale = 0.05 if kind == "bpr" else 0.4
+    user, item, bias, uid, pid, nid = make_problem(rng, U, I, D, B, scale)
+    ok, lr = OPTS[optname]
+    st, dv = slots(ok, ("user", user), ("item", item), ("bias", bias))
+    tu, ti, tb = dev(user), dev(item), dev(bias)
+    # oracle runs in float64 from the float32-rounded inputs
+    user, item, bias = (t.cpu().numpy().astype(np.float64) for t in (tu, ti, tb))
+    st = {k: tuple(None if s is None else dev(s).cpu().numpy().astype(np.float64) for s in v) for k, v in st.items()}
+    k = N.ORX_PAIR_BPR if kind == "bpr" else N.ORX_PAIR_UCML
+    out4 = torch.zeros(4, device="cuda")
+    for step in (1, 2, 3):   # three steps: workspace (hash, staging) must be clean between steps
+        o = N.opt(ok, lr, step=step)
+        eng.pairwise_step(k, N.table(tu, *dv["user"]), N.table(ti, *dv["item"]), N.table(tb, *dv["bias"]),
+                          dev(uid, torch.int32), dev(pid, torch.int32), dev(nid, torch.int32), o, out4,
+                          margin=0.5, c_loss=1.0, c_l2=1.0)
+        loss, l2 = O.pairwise_train_step(kind, user, item, bias, uid, pid, nid, ok, st, step, lr, margin=0.5)
+        close(out4[0], loss, rtol=2e-5, what=f"loss step {step}")
+        close(out4[1], l2, rtol=2e-5, what=f"l2 step {step}")
+        assert out4[2].item() == 0
+        close(tu, user, what=f"user step {step}")
+        close(ti, item, what=f"item step {step}")
+        close(tb, bias, what=f"bias step {step}")
+        for name in ("user", "item", "bias"):
+            for j in (0, 1):
+                if st[name][j] is not None:
+                    close(dv[name][j], st[name][j], what=f"{name} slot{j} step {step}")
+        uid = rng.integers(0, U, B).astype(np.int32)   # new ids each step
+        pid = rng.integers(0, I, B).astype(np.int32)
+        nid = rng.integers(0, I, B).astype(np.int32)
+
+
+def test_pairwise_weighted_objective_and_bad_ids(eng):
+    """tape.gradient(loss + 0.25*l2) and out-of-range ids (counted, triplet skipped)."""
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(5)
+    U, I, D, B = 100, 150, 64, 300
+    user, item, bias, uid, pid, nid = make_problem(rng, U, I, D, B)
+    tu, ti, tb = dev(user), dev(item), dev(bias)
+    user, item, bias = (t.cpu().numpy().astype(np.float64) for t in (tu, ti, tb))
+    bad = uid.copy()
+    bad[7], bad[9] = U + 3, -1
+    out4 = torch.zeros(4, device="cuda")
+    eng.pairwise_step(N.ORX_PAIR_BPR, N.table(tu), N.table(ti), N.table(tb), dev(bad, torch.int32),
+                      dev(pid, torch.int32), dev(nid, torch.int32), N.opt(0, 0.1), out4, c_loss=2.0, c_l2=0.25)
+    assert out4[2].item() == 2
+    keep = np.ones(B, bool)
+    keep[[7, 9]] = False
+    gr = O.bpr_grads(user, item, bias, uid[keep], pid[keep], nid[keep], c_loss=2.0 * keep.sum() / B, c_l2=0.25)
+    for var, name in ((user, "user"), (item, "item"), (bias, "bias")):
+        idx, val = gr[name]
+        O.sgd_sparse(var, idx, val.reshape(len(idx), -1), 0.1)
+    close(tu, user), close(ti, item), close(tb, bias)
+
+
+def test_pairwise_step_host_buffers(eng):
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(6)
+    U, I, D, B = 400, 600, 128, 1024
+    user, item, bias, uid, pid, nid = make_problem(rng, U, I, D, B)
+    tu, ti, tb = dev(user), dev(item), dev(bias)
+    au, ai, ab = (torch.full_like(t, 0.1) for t in (tu, ti, tb))
+    user, item, bias = (t.cpu().numpy().astype(np.float64) for t in (tu, ti, tb))
+    st = {k: (np.full_like(v, 0.1), None) for k, v in (("user", user), ("item", item), ("bias", bias))}
+    hu, hp, hn = (torch.from_numpy(x).pin_memory() for x in (uid, pid, nid))
+    out_h = torch.zeros(4).pin_memory()
+    eng.pairwise_step_host(N.ORX_PAIR_BPR, N.table(tu, au), N.table(ti, ai), N.table(tb, ab), hu, hp, hn,
+                           N.opt(1, 0.05), out_h)
+    torch.cuda.synchronize()
+    loss, l2 = O.pairwise_train_step("bpr", user, item, bias, uid, pid, nid, 1, st, 1, 0.05)
+    np.testing.assert_allclose(out_h[0].item(), loss, rtol=2e-5)
+    np.testing.assert_allclose(out_h[1].item(), l2, rtol=2e-5)
+    close(tu, user), close(ti, item), close(tb, bias), close(ai, st["item"][0])
+
+
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["gmf", "wrmf"])
+def test_pointwise_golden_fwd_grad(eng, golden_dir, kind):
+    from openrec_b200 import native as N
+    g = dict(np.load(os.path.join(golden_dir, f"pointwise_{kind}.npz")))
+    tu, ti, tb = dev(g["user"]), dev(g["item"]), dev(g["bias"])
+    B, D = len(g["uid"]), g["user"].shape[1]
+    uid, iid, lab = dev(g["uid"], torch.int32), dev(g["iid"], torch.int32), dev(g["label"])
+    k = N.ORX_POINT_GMF if kind == "gmf" else N.ORX_POINT_WRMF
+    w = dev(g["w"].reshape(1, -1)) if kind == "gmf" else None
+    wt = N.table(w) if w is not None else None
+    a, b = float(g["a"]), float(g["b"])
+    out4 = torch.zeros(4, device="cuda")
+    eng.pointwise_fwd(k, N.table(tu), N.table(ti), N.table(tb), wt, uid, iid, lab, out4, a, b)
+    close(out4[0], g["loss"], what="loss")
+    close(out4[1], g["l2"], what="l2")
+    du, di = torch.empty(B, D, device="cuda"), torch.empty(B, D, device="cuda")
+    db = torch.empty(B, device="cuda")
+    dw = torch.empty(D, device="cuda") if kind == "gmf" else None
+    eng.pointwise_grad(k, N.table(tu), N.table(ti), N.table(tb), wt, uid, iid, lab, a, b, False, 1.0, 1.0,
+                       d_user=du, d_item=di, d_bias=db, d_w=dw)
+    close(torch.zeros_like(tu).index_add_(0, uid.long(), du), g["g_user"], atol=3e-5)
+    close(torch.zeros_like(ti).index_add_(0, iid.long(), di), g["g_item"], atol=3e-5)
+    close(torch.zeros(len(g["bias"]), device="cuda").index_add_(0, iid.long(), db), g["g_bias"], atol=3e-5)
+    if kind == "gmf":
+        close(dw, g["g_w"], what="g_w")
+
+
+@pytest.mark.parametrize("kind", ["gmf", "wrmf"])
+@pytest.mark.parametrize("optname", list(OPTS))
+@pytest.mark.parametrize("D,U,I,B", [(10, 29, 41, 80), (64, 700, 900, 1000), (128, 3000, 4000, 2048)])
+def test_pointwise_step(eng, kind, optname, D, U, I, B):
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(hash((kind, optname, D)) % 2**31)
+    user, item, bias, uid, iid, _ = make_problem(rng, U, I, D, B, 0.3)
+    label = (rng.random(B) < 0.4).astype(np.float32)
+    w = rng.uniform(-0.3, 0.3, (1, D))
+    ok, lr = OPTS[optname]
+    a, b, sig = (1.0, 1.0, False) if kind == "gmf" else (3.0, 0.5, D == 64)
+    st, dv = slots(ok, ("user", user), ("item", item), ("bias", bias), ("w", w))
+    tu, ti, tb, tw = dev(user), dev(item), dev(bias), dev(w)
+    user, item, bias, w = (t.cpu().numpy().astype(np.float64) for t in (tu, ti, tb, tw))
+    st = {k: tuple(None if s is None else dev(s).cpu().numpy().astype(np.float64) for s in v) for k, v in st.items()}
+    k = N.ORX_POINT_GMF if kind == "gmf" else N.ORX_POINT_WRMF
+    out4 = torch.zeros(4, device="cuda")
+    for step in (1, 2):
+        wt = N.table(tw, *dv["w"]) if kind == "gmf" else None
+        eng.pointwise_step(k, N.table(tu, *dv["user"]), N.table(ti, *dv["item"]), N.table(tb, *dv["bias"]), wt,
+                           dev(uid, torch.int32), dev(iid, torch.int32), dev(label), N.opt(ok, lr, step=step), out4,
+                           a, b, sig)
+        loss, l2 = O.pointwise_train_step(kind, user, item, bias, w.reshape(-1, 1) if kind == "gmf" else None, uid, iid,
+                                          label, ok, {**st, "w": tuple(None if s is None else s.reshape(-1, 1)
+                                                                       for s in st["w"])},
+                                          step, lr, a, b, sig) if kind == "gmf" else \
+            O.pointwise_train_step(kind, user, item, bias, None, uid, iid, label, ok, st, step, lr, a, b, sig)
+        close(out4[0], loss, rtol=2e-5, what="loss")
+        close(out4[1], l2, rtol=2e-5, what="l2")
+        close(tu, user, what="user"), close(ti, item, what="item"), close(tb, bias, what="bias")
+        if kind == "gmf":
+            close(tw, w, what="w")
+        for name in ("user", "item", "bias"):
+            for j in (0, 1):
+                if st[name][j] is not None:
+                    close(dv[name][j], st[name][j], what=f"{name} slot{j}")
+        uid = rng.integers(0, U, B).astype(np.int32)
+        iid = rng.integers(0, I, B).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------
+def test_gather_bit_exact(eng):
+    rng = np.random.default_rng(1)
+    tab = rng.standard_normal((1000, 50)).astype(np.float32)
+    ids = rng.integers(0, 1000, 777)
+    for dt in (torch.int32, torch.int64):
+        out = eng.gather(dev(tab), dev(ids, dt))
+        assert np.array_equal(out.cpu().numpy(), tab[ids])   # gather must be bit-exact
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ids2 = ids.copy()
+    ids2[3] = 5000
+    out = eng.gather(dev(tab), dev(ids2, torch.int32), bad)
+    assert bad.item() == 1 and not out[3].any()
+
+
+def test_censor(eng, golden_dir):
+    g = dict(np.load(os.path.join(golden_dir, "pairwise_ucml.npz")))
+    tu, ti = dev(g["user"]), dev(g["item"])
+    eng.censor(tu, dev(g["uid"], torch.int32))
+    eng.censor(ti, dev(g["pid"], torch.int32))
+    eng.censor(ti, dev(g["nid"], torch.int32))
+    close(tu, g["user_censored"]), close(ti, g["item_censored"])
+    rng = np.random.default_rng(2)
+    tab = rng.standard_normal((50, 128)) * 0.001   # tiny rows: max(norm, 0.1) branch
+    t = dev(tab)
+    ids = rng.integers(0, 50, 400).astype(np.int32)   # many duplicates: each row scaled exactly once
+    eng.censor(t, dev(ids, torch.int32))
+    ref = t.new_tensor(tab).cpu().numpy().astype(np.float64)
+    O.censor(ref, ids)
+    close(t, ref)
+
+
+def test_score_all_and_metrics(eng, golden_dir):
+    from openrec_b200 import native as N
+    for kind, name in ((N.ORX_SCORE_DOT, "pairwise_bpr"), (N.ORX_SCORE_NEG_SQDIST, "pairwise_ucml")):
+        g = dict(np.load(os.path.join(golden_dir, f"{name}.npz")))
+        s = eng.score_all(kind, dev(g["user"]), dev(g["uid"][:5], torch.int32), dev(g["item"]), dev(g["bias"]))
+        close(s, g["inference"], atol=1e-4 if kind else ATOL)
+    g = dict(np.load(os.path.join(golden_dir, "pointwise_gmf.npz")))
+    s = eng.score_all(N.ORX_SCORE_DOT, dev(g["user"]), dev(g["uid"][:5], torch.int32), dev(g["item"]),
+                      dev(g["bias"]), scale=dev(g["w"].reshape(-1)))
+    close(s, g["inference"])
+    m = dict(np.load(os.path.join(golden_dir, "metrics.npz")))
+    auc, ndcg, rec = eng.rank_metrics(dev(m["pred"]), dev(m["pos"], torch.uint8), dev(m["excl"], torch.uint8),
+                                      at=(5, 20))
+    close(auc, m["auc"], atol=1e-6), close(ndcg, m["ndcg"], atol=1e-5), close(rec, m["recall"], atol=1e-6)
+    # bigger random case against the oracle
+    rng = np.random.default_rng(3)
+    R, I = 9, 17000
+    pred = rng.standard_normal((R, I)).astype(np.float32)
+    pos = rng.random((R, I)) < 0.002
+    pos[:, 7] = True
+    excl = (rng.random((R, I)) < 0.01) & ~pos
+    auc, ndcg, rec = eng.rank_metrics(dev(pred), dev(pos, torch.uint8), dev(excl, torch.uint8), at=(50, 100))
+    close(auc, O.auc(pos, pred, excl), atol=1e-6)
+    close(ndcg, O.ndcg(pos, pred, excl, (50, 100)), atol=1e-4)
+    close(rec, O.recall(pos, pred, excl, (50, 100)), atol=1e-6)
+
+
+def test_dense_apply_and_fill(eng):
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(4)
+    n = 5000
+    for ok, lr in OPTS.values():
+        var, grad = rng.standard_normal(n), rng.standard_normal(n)
+        s0, s1 = np.abs(rng.standard_normal(n)) * 0.1 + 0.1, np.abs(rng.standard_normal(n)) * 0.1 + 0.01
+        tv, tg, t0, t1 = dev(var), dev(grad), dev(s0), dev(s1)
+        var, grad, s0, s1 = (t.cpu().numpy().astype(np.float64) for t in (tv, tg, t0, t1))
+        eng.dense_apply(tv, t0 if ok else None, t1 if ok >= 2 else None, tg, N.opt(ok, lr, step=4))
+        O.apply_dense(ok, var, s0, s1, grad, 4, lr)
+        close(tv, var)
+    t = torch.empty(1 << 20, device="cuda")
+    eng.fill_uniform(t, -0.05, 0.05, 123)
+    assert t.min().item() >= -0.05 and t.max().item() < 0.05
+    assert abs(t.mean().item()) < 2e-4 and abs(t.std().item() - 0.1 / 12 ** 0.5) < 2e-4
+    t2 = torch.empty_like(t)
+    eng.fill_uniform(t2, -0.05, 0.05, 123)
+    assert torch.equal(t, t2)
+
+
+def test_full_size_bpr_adagrad(eng):
+    """BASELINE.json configs[1]: 1M x 1M, D=128, B=65536; oracle on the touched rows."""
+    from openrec_b200 import native as N
+    U = I = 1_000_000
+    D, B = 128, 65536
+    tu, ti = torch.empty(U, D, device="cuda"), torch.empty(I, D, device="cuda")
+    tb = torch.empty(I, 1, device="cuda")
+    eng.fill_uniform(tu, -0.05, 0.05, 1), eng.fill_uniform(ti, -0.05, 0.05, 2), eng.fill_uniform(tb, -0.05, 0.05, 3)
+    au, ai, ab = (torch.full_like(t, 0.1) for t in (tu, ti, tb))
+    g = torch.Generator(device="cpu").manual_seed(1)
+    uid, pid, nid = (torch.randint(0, U, (B,), generator=g, dtype=torch.int32) for _ in range(3))
+    rows_u, rows_i = np.unique(uid.numpy()), np.unique(np.concatenate([pid.numpy(), nid.numpy()]))
+    # compact oracle problem over the touched rows only
+    mu = {r: k for k, r in enumerate(rows_u)}
+    mi = {r: k for k, r in enumerate(rows_i)}
+    cu = np.array([mu[r] for r in uid.numpy()], dtype=np.int32)
+    cp = np.array([mi[r] for r in pid.numpy()], dtype=np.int32)
+    cn = np.array([mi[r] for r in nid.numpy()], dtype=np.int32)
+    user = tu[torch.from_numpy(rows_u).cuda()].cpu().numpy().astype(np.float64)
+    item = ti[torch.from_numpy(rows_i).cuda()].cpu().numpy().astype(np.float64)
+    bias = tb[torch.from_numpy(rows_i).cuda()].cpu().numpy().astype(np.float64)
+    st = {k: (np.full_like(v, 0.1), None) for k, v in (("user", user), ("item", item), ("bias", bias))}
+    untouched_before = ti[:1000].clone()
+    out4 = torch.zeros(4, device="cuda")
+    eng.pairwise_step(N.ORX_PAIR_BPR, N.table(tu, au), N.table(ti, ai), N.table(tb, ab), uid.cuda(), pid.cuda(),
+                      nid.cuda(), N.opt(1, 0.05), out4)
+    loss, l2 = O.pairwise_train_step("bpr", user, item, bias, cu, cp, cn, 1, st, 1, 0.05)
+    close(out4[0], loss, rtol=2e-5), close(out4[1], l2, rtol=2e-5)
+    n_dup = int((np.unique(uid.numpy(), return_counts=True)[1] > 1).sum()
+                + (np.unique(np.concatenate([pid.numpy(), nid.numpy()]), return_counts=True)[1] > 1).sum())
+    assert out4[3].item() == n_dup   # exactly the duplicated rows were staged
+    close(tu[torch.from_numpy(rows_u).cuda()], user)
+    close(ti[torch.from_numpy(rows_i).cuda()], item)
+    close(tb[torch.from_numpy(rows_i).cuda()], bias)
+    close(ai[torch.from_numpy(rows_i).cuda()], st["item"][0])
+    mask = torch.ones(1000, dtype=torch.bool)
+    mask[torch.from_numpy(rows_i[rows_i < 1000])] = False
+    assert torch.equal(ti[:1000][mask.cuda()], untouched_before[mask.cuda()])   # untouched rows bit-identical
