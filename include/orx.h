@@ -78,6 +78,13 @@ ORX_API int orx_device_count(int* n_out_host);
 /* Blocks the host until `stream` has drained (cudaStreamSynchronize). */
 ORX_API int orx_stream_synchronize(orx_handle_t h, orx_stream_t stream);
 
+/* Measurement hook (bench.py's roofline): while enabled, every *_step call records CUDA events on its
+ * launch stream around its kernels -- [0] batch index build, [1] the fused gather-score-update kernel,
+ * [2] tail (+ Adam sweep).  orx_profile_read waits for the recorded events, returns the summed device
+ * time per phase (ms) and the number of steps recorded since the last read, and resets the counters. */
+ORX_API int orx_profile_enable(orx_handle_t h, int32_t on);
+ORX_API int orx_profile_read(orx_handle_t h, float* ms3_host, int32_t* n_steps_host);
+
 /* ---- LatentFactor ---------------------------------------------------------------------- */
 /* LatentFactor.__init__ 'uniform' initializer = U(-0.05,0.05), on device, counter-based RNG
  * (latent_factor.py:8-15).  lo/hi generalise it (glorot for MLP kernels). */

@@ -60,7 +60,18 @@ struct orx_ctx {
   float* out_stage[2];
   int64_t stage_cap;
   uint32_t stage_flip;
+  // measurement hook (orx_profile_*)
+  int prof_on, prof_n, prof_cap;
+  cudaEvent_t* prof_ev;  // [prof_cap*4]
 };
+
+// record phase boundary k (0..3) of the current step on `st` when profiling is enabled
+static inline void orx_prof_mark(orx_ctx* c, int k, cudaStream_t st) {
+  if (c->prof_on && c->prof_n < c->prof_cap) cudaEventRecord(c->prof_ev[c->prof_n * 4 + k], st);
+}
+static inline void orx_prof_next(orx_ctx* c) {
+  if (c->prof_on && c->prof_n < c->prof_cap) c->prof_n++;
+}
 
 int orx_ensure_workspace(orx_ctx* c, int64_t B, int32_t dim, bool full_staging);
 int orx_ensure_stage(orx_ctx* c, int64_t n_ints);

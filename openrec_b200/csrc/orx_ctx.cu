@@ -147,7 +147,41 @@ extern "C" int orx_destroy(orx_handle_t h) {
   }
   cudaFree(h->counters);
   cudaFree(h->partials);
+  if (h->prof_ev) {
+    for (int i = 0; i < h->prof_cap * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev;
+  }
   delete h;
+  return ORX_OK;
+}
+
+extern "C" int orx_profile_enable(orx_handle_t h, int32_t on) {
+  ORX_REQUIRE(h != nullptr, "null handle");
+  ORX_CUDA(cudaSetDevice(h->device));
+  if (on && !h->prof_ev) {
+    h->prof_cap = 4096;
+    h->prof_ev = new cudaEvent_t[h->prof_cap * 4];
+    for (int i = 0; i < h->prof_cap * 4; ++i) ORX_CUDA(cudaEventCreate(&h->prof_ev[i]));
+  }
+  h->prof_on = on ? 1 : 0;
+  h->prof_n = 0;
+  return ORX_OK;
+}
+
+extern "C" int orx_profile_read(orx_handle_t h, float* ms3, int32_t* n_steps) {
+  ORX_REQUIRE(h != nullptr && ms3 && n_steps, "null pointer");
+  ORX_CUDA(cudaSetDevice(h->device));
+  ms3[0] = ms3[1] = ms3[2] = 0.f;
+  *n_steps = h->prof_n;
+  for (int i = 0; i < h->prof_n; ++i) {
+    ORX_CUDA(cudaEventSynchronize(h->prof_ev[i * 4 + 3]));
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      ORX_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[i * 4 + k], h->prof_ev[i * 4 + k + 1]));
+      ms3[k] += ms;
+    }
+  }
+  h->prof_n = 0;
   return ORX_OK;
 }
 

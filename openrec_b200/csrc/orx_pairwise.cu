@@ -656,7 +656,9 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
   const int D = user->dim;
   if ((rc = orx_ensure_workspace(c, B, D, opt->kind == ORX_OPT_ADAM_DENSE))) return rc;
   const bool dense = opt->kind == ORX_OPT_ADAM_DENSE;
+  orx_prof_mark(c, 0, st);
   if ((rc = orx_launch_index_build(c, uid, user->rows, B, pid, nid, item->rows, B, dense, st))) return rc;
+  orx_prof_mark(c, 1, st);
 
   PairArgs pa;
   pa.U = user->var; pa.Us0 = user->s0; pa.Us1 = user->s1;
@@ -674,6 +676,7 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
   rc = (kind == ORX_PAIR_BPR) ? launch_pair_step_kind<ORX_PAIR_BPR>(pa, opt->kind, st, &n_partials)
                               : launch_pair_step_kind<ORX_PAIR_UCML>(pa, opt->kind, st, &n_partials);
   if (rc) return rc;
+  orx_prof_mark(c, 2, st);
   if (dense) {
     if ((rc = orx_launch_adam_sweep(c, user->var, user->s0, user->s1, user->rows, D, c->hu, c->gu, pa.opt, st))) return rc;
     if ((rc = orx_launch_adam_sweep(c, item->var, item->s0, item->s1, item->rows, D, c->hi, c->gi, pa.opt, st))) return rc;
@@ -689,7 +692,10 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
   ta.loss_scale = (kind == ORX_PAIR_BPR) ? pa.inv_B : 1.0f;
   ta.counters = c->counters; ta.out4 = out4;
   ta.W = ta.Ws0 = ta.Ws1 = ta.gw = nullptr; ta.c_l2 = c_l2;
-  return orx_launch_tail(c, ta, opt->kind, st);
+  rc = orx_launch_tail(c, ta, opt->kind, st);
+  orx_prof_mark(c, 3, st);
+  orx_prof_next(c);
+  return rc;
 }
 
 extern "C" int orx_pairwise_step(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,

@@ -70,6 +70,17 @@ class Engine:
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # ---- measurement hook ----
+    def profile_enable(self, on=True):
+        _lib.check(self.lib.orx_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> ([ms_index, ms_step, ms_tail] summed over the recorded steps, n_steps)."""
+        ms = (C.c_float * 3)()
+        n = C.c_int32()
+        _lib.check(self.lib.orx_profile_read(self.h, ms, C.byref(n)))
+        return [ms[0], ms[1], ms[2]], n.value
+
     # ---- LatentFactor ------------------------------------------------------------------
     def fill_uniform(self, dst, lo, hi, seed):
         _lib.check(self.lib.orx_fill_uniform(self.h, _ptr(_f32(dst, "dst")), dst.numel(), lo, hi, seed, self.stream()))

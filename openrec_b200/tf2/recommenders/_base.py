@@ -1,0 +1,66 @@
+"""Shared machinery of the fused-step recommenders (BPR, UCML, GMF, WRMF).
+
+The step protocol (tf2_examples/bpr_citeulike.py:33-39) is executed as ONE liborx call when
+``optimizer.apply_gradients`` receives the full symbolic gradient set of a step node; see
+openrec_b200/tfshim/core.py."""
+from __future__ import annotations
+
+import torch
+
+from ... import native as N
+from ..._lib import OrxTable
+from ...tfshim.core import LazyScalar, StepNode, Tensor, convert
+from ...tfshim.keras import Model
+
+
+def ids_of(x):
+    """int32 device ids from whatever the caller feeds (Keras Embedding casts to int32)."""
+    return N.ids32(convert(x).t)
+
+
+class FusedRecommender(Model):
+    """Base: subclasses define the kernels behind _orx_forward / _orx_run_step / _orx_run_grad."""
+
+    def _tables(self, optimizer=None):
+        vs = (self.user_latent_factor.embeddings, self.item_latent_factor.embeddings, self.item_bias.embeddings)
+        if optimizer is None:
+            return tuple(N.table(v.t) for v in vs)
+        return tuple(optimizer.table(v) for v in vs)
+
+    def _orx_step_variables(self):
+        return self.trainable_variables
+
+    def _new_node(self, *ids):
+        if self.user_latent_factor.output_dim != self.item_latent_factor.output_dim:
+            raise ValueError("user and item embedding dims must match (the reference multiplies them elementwise)")
+        node = StepNode(self, 2)
+        node.ids = ids
+        return node, LazyScalar(node, {0: 1.0}), LazyScalar(node, {1: 1.0})
+
+    def _orx_apply(self, node, grads_and_vars, optimizer):
+        if node.stepped:
+            raise RuntimeError("this model call's gradients were already applied")
+        want = {id(v) for v in self._orx_step_variables()}
+        got = {id(v) for _, v in grads_and_vars}
+        coefs = [g.coef for g, _ in grads_and_vars]
+        if got != want or any(c != coefs[0] for c in coefs):
+            raise NotImplementedError(
+                "apply_gradients: the fused step needs the gradients of ALL of the model's trainable variables "
+                "w.r.t. one objective (as tape.gradient(loss, model.trainable_variables) returns them)")
+        c_loss, c_l2 = float(coefs[0].get(0, 0.0)), float(coefs[0].get(1, 0.0))
+        if node.out is None:
+            node.out = torch.zeros(4, dtype=torch.float32, device=node.ids[0].device)
+        self._orx_run_step(node, optimizer, c_loss, c_l2)
+        node.stepped = True
+
+    def _orx_materialize_grad(self, node, var, coef):
+        """IndexedSlices (indices, values) of d(objective)/d(var), not deduplicated (TF form)."""
+        if node.stepped:
+            raise RuntimeError("gradients requested after the step was applied (tables already updated)")
+        return self._orx_run_grad(node, var, float(coef.get(0, 0.0)), float(coef.get(1, 0.0)))
+
+
+def w_table(var, s0=None, s1=None):
+    """GMF's Dense(1) kernel [D,1] viewed as a 1-row table (rows=1, dim=D)."""
+    return OrxTable(var.data_ptr(), s0.data_ptr() if s0 is not None else None,
+                    s1.data_ptr() if s1 is not None else None, 1, var.numel())

@@ -2,6 +2,7 @@
 Bar: indices bit-exact (out-of-range / duplicate handling), loss / gradients / updated rows
 within 1e-5 (fp32) of the oracle evaluated in float64 on identical weights and ids."""
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -23,6 +24,25 @@ def eng():
 
 def dev(a, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(a)).to("cuda", dtype)
+
+
+def seed_of(*parts):
+    return zlib.crc32(repr(parts).encode())   # hash() is randomised per process
+
+
+def avoid_hinge_ties(rng, user, item, bias, uid, pid, nid, margin=0.5, tol=1e-3):
+    """UCML's hinge is discontinuous in its gradient: a triplet with |h| ~ 1e-7 may be active in
+    float32 and inactive in float64.  Parity is only defined away from the kink, so resample the
+    negatives of such triplets (the reference has the same measure-zero ambiguity)."""
+    for _ in range(20):
+        u, p, n = user[uid], item[pid], item[nid]
+        h = margin - ((-((u - p) ** 2).sum(1) + bias[pid, 0]) - (-((u - n) ** 2).sum(1) + bias[nid, 0]))
+        bad = np.abs(h) < tol
+        if not bad.any():
+            return nid
+        nid = nid.copy()
+        nid[bad] = rng.integers(0, len(item), bad.sum())
+    raise AssertionError("could not avoid hinge ties")
 
 
 def make_problem(rng, U, I, D, B, scale=0.05):
@@ -92,7 +112,7 @@ def test_pairwise_golden_fwd_grad(eng, golden_dir, kind):
                                      (128, 5000, 9000, 4096), (256, 500, 700, 333)])
 def test_pairwise_step(eng, kind, optname, D, U, I, B):
     from openrec_b200 import native as N
-    rng = np.random.default_rng(hash((kind, optname, D)) % 2**31)
+    rng = np.random.default_rng(seed_of(kind, optname, D))
     scale = 0.05 if kind == "bpr" else 0.4
     user, item, bias, uid, pid, nid = make_problem(rng, U, I, D, B, scale)
     ok, lr = OPTS[optname]
@@ -104,6 +124,8 @@ def test_pairwise_step(eng, kind, optname, D, U, I, B):
     k = N.ORX_PAIR_BPR if kind == "bpr" else N.ORX_PAIR_UCML
     out4 = torch.zeros(4, device="cuda")
     for step in (1, 2, 3):   # three steps: workspace (hash, staging) must be clean between steps
+        if kind == "ucml":
+            nid = avoid_hinge_ties(rng, user, item, bias, uid, pid, nid)
         o = N.opt(ok, lr, step=step)
         eng.pairwise_step(k, N.table(tu, *dv["user"]), N.table(ti, *dv["item"]), N.table(tb, *dv["bias"]),
                           dev(uid, torch.int32), dev(pid, torch.int32), dev(nid, torch.int32), o, out4,
@@ -200,7 +222,7 @@ def test_pointwise_golden_fwd_grad(eng, golden_dir, kind):
 @pytest.mark.parametrize("D,U,I,B", [(10, 29, 41, 80), (64, 700, 900, 1000), (128, 3000, 4000, 2048)])
 def test_pointwise_step(eng, kind, optname, D, U, I, B):
     from openrec_b200 import native as N
-    rng = np.random.default_rng(hash((kind, optname, D)) % 2**31)
+    rng = np.random.default_rng(seed_of(kind, optname, D))
     user, item, bias, uid, iid, _ = make_problem(rng, U, I, D, B, 0.3)
     label = (rng.random(B) < 0.4).astype(np.float32)
     w = rng.uniform(-0.3, 0.3, (1, D))
