@@ -122,11 +122,19 @@ ORX_API int orx_pairwise_fwd(orx_handle_t h, int32_t kind, const orx_table_t* us
                      int32_t B, float margin, float* out4, orx_stream_t s);
 /* Un-fused gradients in TF IndexedSlices form (values per lookup, NOT deduplicated):
  * d_user[B,D], d_pos[B,D], d_neg[B,D], d_bp[B], d_bn[B]; any may be NULL.  g_out[B] (optional) receives
- * the per-triplet loss-gradient scalar. */
+ * the per-triplet loss-gradient scalar.  orx_pairwise_grad_slots is the compact form used by the sharded
+ * step: the "tables" are the rows fetched for this batch (one row per lookup), gradients are written to
+ * the lookup's own row (d_user[uid[t]], d_item[pid[t]] / d_item[nid[t]], d_bias likewise), and out4 gets
+ * the local (loss, l2_loss) sums. */
 ORX_API int orx_pairwise_grad(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
                       const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
                       int32_t B, float margin, float c_loss, float c_l2, float* d_user, float* d_pos, float* d_neg,
                       float* d_bp, float* d_bn, float* g_out, orx_stream_t s);
+
+ORX_API int orx_pairwise_grad_slots(orx_handle_t h, int32_t kind, const float* user_rows, const float* item_rows,
+                            const float* bias_rows, int32_t dim, const int32_t* uslot, const int32_t* pslot,
+                            const int32_t* nslot, int32_t B, float margin, float c_loss, float c_l2, float inv_B,
+                            float* d_user_rows, float* d_item_rows, float* d_bias_rows, float* out4, orx_stream_t s);
 
 /* ---- pointwise recommenders: GMF (recommenders/gmf.py:22-34) and WRMF (recommenders/wrmf.py:21-34 +
  *      modules/pointwise_mse_loss.py:18-31) ---------------------------------------------------
@@ -145,6 +153,17 @@ ORX_API int orx_pointwise_grad(orx_handle_t h, int32_t kind, const orx_table_t* 
                        const float* label, int32_t B, float a, float b, int32_t use_sigmoid, float c_loss,
                        float c_l2, float* d_user, float* d_item, float* d_bias, float* d_w, float* g_out,
                        orx_stream_t s);
+
+/* ---- un-fused sparse apply + multi-GPU building blocks (the reference is single-device) ----
+ * orx_sparse_apply: optimizer.apply_gradients for ONE variable given IndexedSlices (ids[n], values[n,dim]):
+ * dedup by row, apply once per unique row (what Keras OptimizerV2 does for every tape.gradient result of
+ * an Embedding, tf2_examples/bpr_citeulike.py:37-38).  Used by owners in the row-sharded step and by DLRM. */
+ORX_API int orx_sparse_apply(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
+                             int32_t n, const orx_opt_t* opt_host, orx_stream_t s);
+/* orx_owner_bucket: row r lives on rank r % world at local row r / world.  counts[world] = lookups per owner,
+ * send_local[n] = local rows in owner-sorted send order, slot[n] = position of lookup i in that order. */
+ORX_API int orx_owner_bucket(orx_handle_t h, const int32_t* ids, int32_t n, int32_t world, int32_t* counts,
+                             int32_t* send_local, int32_t* slot, orx_stream_t s);
 
 /* ---- dense variables (GMF w, MLP kernels/biases): Keras dense apply ---------------------- */
 ORX_API int orx_dense_apply(orx_handle_t h, float* var, float* s0, float* s1, const float* grad, int64_t n,

@@ -147,6 +147,7 @@ extern "C" int orx_destroy(orx_handle_t h) {
   }
   cudaFree(h->counters);
   cudaFree(h->partials);
+  cudaFree(h->bucket_cursor);
   if (h->prof_ev) {
     for (int i = 0; i < h->prof_cap * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;

@@ -13,6 +13,8 @@
 //          red.global.add'ed into the compact staging buffer (so every gather sees pre-step values).
 //   3. k_pair_tail   : optimizer for the staged rows (once per unique row), staging re-zeroed,
 //                      hash cleared, deterministic loss reduction.
+#include <stdlib.h>
+
 #include "orx_common.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -126,15 +128,19 @@ struct TripRegs {
 };
 
 // flags: bit0 triplet valid, bit1/2/3 user/pos/neg row owned by this triplet (fast path)
-template <int KIND, int OPT, int D, int CH>
-__global__ void __launch_bounds__(256) k_pair_step(const PairArgs a) {
+//
+// One warp owns CH consecutive triplets.  Order of issue inside a warp (latency first):
+//   ids (coalesced, lanes < CH) -> variable rows of the first one/two triplet groups (they need only
+//   the ids) -> hash probes + bias loads (lanes < CH, overlap the row loads) -> slot rows of the first
+//   groups -> steady state: process one register buffer while the other's 128-bit loads are in flight.
+template <int KIND, int OPT, int D, int CH, int MINB, bool PIPE>
+__global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
   constexpr int G = (D / 4 < 32) ? D / 4 : 32;  // lanes per triplet
   constexpr int K = D / (4 * G);                // float4 per lane per row
   constexpr int TPW = 32 / G;                   // triplets in flight per warp
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool STAGE_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
-  constexpr bool PIPE = !S1;  // register double-buffering (too many registers with Adam's 9 rows)
   static_assert(CH % TPW == 0, "chunk must be a multiple of the triplets per warp");
   typedef TripRegs<K, S0, S1> Regs;
 
@@ -142,67 +148,83 @@ __global__ void __launch_bounds__(256) k_pair_step(const PairArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int grp = lane / G, gl = lane % G;
   const int t = warp * CH + lane;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  // ---- per-lane metadata of triplet t (lanes < CH)
+  // ---- ids of triplet t (lanes < CH)
   int u_id = 0, p_id = 0, n_id = 0, du = -1, dp = -1, dn = -1, flags = 0;
-  float bp = 0.f, bn = 0.f, bps0 = 0.f, bps1 = 0.f, bns0 = 0.f, bns1 = 0.f;
   if (lane < CH && t < a.B) {
     u_id = a.uid[t];
     p_id = a.pid[t];
     n_id = a.nid[t];
-    const bool ok = u_id >= 0 && u_id < a.rowsU && p_id >= 0 && p_id < a.rowsI && n_id >= 0 && n_id < a.rowsI;
-    if (ok) {
-      const uint32_t cu = orx_hash_find(a.hu, u_id, &du);
-      const uint32_t cp = orx_hash_find(a.hi, p_id, &dp);
-      const uint32_t cn = orx_hash_find(a.hi, n_id, &dn);
-      bp = __ldcg(a.Bv + p_id);
-      bn = __ldcg(a.Bv + n_id);
-      flags = 1;
-      if (!STAGE_ONLY) {
-        flags |= (cu == 1u ? 2 : 0) | (cp == 1u ? 4 : 0) | (cn == 1u ? 8 : 0);
-        if (S0) {
-          if (flags & 4) bps0 = __ldcg(a.Bs0 + p_id);
-          if (flags & 8) bns0 = __ldcg(a.Bs0 + n_id);
-        }
-        if (S1) {
-          if (flags & 4) bps1 = __ldcg(a.Bs1 + p_id);
-          if (flags & 8) bns1 = __ldcg(a.Bs1 + n_id);
-        }
+    flags = (u_id >= 0 && u_id < a.rowsU && p_id >= 0 && p_id < a.rowsI && n_id >= 0 && n_id < a.rowsI) ? 1 : 0;
+  }
+
+  // variable rows: need ids + the valid bit only
+  auto load_var = [&](int j, Regs& r) {
+    const int src = j + grp;
+    r.fl = __shfl_sync(ORX_FULL, flags, src) & 1;
+    r.uu = __shfl_sync(ORX_FULL, u_id, src);
+    r.pp = __shfl_sync(ORX_FULL, p_id, src);
+    r.nn = __shfl_sync(ORX_FULL, n_id, src);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int off = (k * G + gl) * 4;
+      r.u[k] = r.fl ? __ldcg(reinterpret_cast<const float4*>(a.U + (int64_t)r.uu * D + off)) : z4;
+      r.p[k] = r.fl ? __ldcg(reinterpret_cast<const float4*>(a.I + (int64_t)r.pp * D + off)) : z4;
+      r.n[k] = r.fl ? __ldcg(reinterpret_cast<const float4*>(a.I + (int64_t)r.nn * D + off)) : z4;
+    }
+  };
+  Regs ra, rb;
+  load_var(0, ra);
+  if (PIPE && TPW < CH) load_var(TPW, rb);
+
+  // ---- hash probes + item_bias (lanes < CH), overlapping the row loads above
+  float bp = 0.f, bn = 0.f, bps0 = 0.f, bps1 = 0.f, bns0 = 0.f, bns1 = 0.f;
+  if (flags & 1) {
+    const uint32_t cu = orx_hash_find(a.hu, u_id, &du);
+    const uint32_t cp = orx_hash_find(a.hi, p_id, &dp);
+    const uint32_t cn = orx_hash_find(a.hi, n_id, &dn);
+    bp = __ldcg(a.Bv + p_id);
+    bn = __ldcg(a.Bv + n_id);
+    if (!STAGE_ONLY) {
+      flags |= (cu == 1u ? 2 : 0) | (cp == 1u ? 4 : 0) | (cn == 1u ? 8 : 0);
+      if (S0) {
+        if (flags & 4) bps0 = __ldcg(a.Bs0 + p_id);
+        if (flags & 8) bns0 = __ldcg(a.Bs0 + n_id);
+      }
+      if (S1) {
+        if (flags & 4) bps1 = __ldcg(a.Bs1 + p_id);
+        if (flags & 8) bns1 = __ldcg(a.Bs1 + n_id);
       }
     }
   }
 
-  auto load = [&](int j, Regs& r) {
+  // optimizer-slot rows + staging indices: need the probe results
+  auto load_slots = [&](int j, Regs& r) {
     const int src = j + grp;
     r.fl = __shfl_sync(ORX_FULL, flags, src);
-    r.uu = __shfl_sync(ORX_FULL, u_id, src);
-    r.pp = __shfl_sync(ORX_FULL, p_id, src);
-    r.nn = __shfl_sync(ORX_FULL, n_id, src);
     r.du = __shfl_sync(ORX_FULL, du, src);
     r.dp = __shfl_sync(ORX_FULL, dp, src);
     r.dn = __shfl_sync(ORX_FULL, dn, src);
     r.bp = __shfl_sync(ORX_FULL, bp, src);
     r.bn = __shfl_sync(ORX_FULL, bn, src);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int off = (k * G + gl) * 4;
-      const bool v = r.fl & 1;
-      r.u[k] = v ? __ldcg(reinterpret_cast<const float4*>(a.U + (int64_t)r.uu * D + off)) : z;
-      r.p[k] = v ? __ldcg(reinterpret_cast<const float4*>(a.I + (int64_t)r.pp * D + off)) : z;
-      r.n[k] = v ? __ldcg(reinterpret_cast<const float4*>(a.I + (int64_t)r.nn * D + off)) : z;
       if (S0) {
-        r.us0[k] = (r.fl & 2) ? __ldcg(reinterpret_cast<const float4*>(a.Us0 + (int64_t)r.uu * D + off)) : z;
-        r.ps0[k] = (r.fl & 4) ? __ldcg(reinterpret_cast<const float4*>(a.Is0 + (int64_t)r.pp * D + off)) : z;
-        r.ns0[k] = (r.fl & 8) ? __ldcg(reinterpret_cast<const float4*>(a.Is0 + (int64_t)r.nn * D + off)) : z;
+        r.us0[k] = (r.fl & 2) ? __ldcg(reinterpret_cast<const float4*>(a.Us0 + (int64_t)r.uu * D + off)) : z4;
+        r.ps0[k] = (r.fl & 4) ? __ldcg(reinterpret_cast<const float4*>(a.Is0 + (int64_t)r.pp * D + off)) : z4;
+        r.ns0[k] = (r.fl & 8) ? __ldcg(reinterpret_cast<const float4*>(a.Is0 + (int64_t)r.nn * D + off)) : z4;
       }
       if (S1) {
-        r.us1[k] = (r.fl & 2) ? __ldcg(reinterpret_cast<const float4*>(a.Us1 + (int64_t)r.uu * D + off)) : z;
-        r.ps1[k] = (r.fl & 4) ? __ldcg(reinterpret_cast<const float4*>(a.Is1 + (int64_t)r.pp * D + off)) : z;
-        r.ns1[k] = (r.fl & 8) ? __ldcg(reinterpret_cast<const float4*>(a.Is1 + (int64_t)r.nn * D + off)) : z;
+        r.us1[k] = (r.fl & 2) ? __ldcg(reinterpret_cast<const float4*>(a.Us1 + (int64_t)r.uu * D + off)) : z4;
+        r.ps1[k] = (r.fl & 4) ? __ldcg(reinterpret_cast<const float4*>(a.Is1 + (int64_t)r.pp * D + off)) : z4;
+        r.ns1[k] = (r.fl & 8) ? __ldcg(reinterpret_cast<const float4*>(a.Is1 + (int64_t)r.nn * D + off)) : z4;
       }
     }
   };
+  load_slots(0, ra);
+  if (PIPE && TPW < CH) load_slots(TPW, rb);
 
   float loss_acc = 0.f, l2_acc = 0.f, g_own = 0.f;
 
@@ -269,21 +291,28 @@ __global__ void __launch_bounds__(256) k_pair_step(const PairArgs a) {
   };
 
   if (PIPE) {
-    Regs ra, rb;
-    load(0, ra);
 #pragma unroll 1
     for (int j = 0; j < CH; j += 2 * TPW) {
-      const bool has_b = (j + TPW < CH);
-      if (has_b) load(j + TPW, rb);
       process(j, ra);
-      if (j + 2 * TPW < CH) load(j + 2 * TPW, ra);
-      if (has_b) process(j + TPW, rb);
+      if (j + 2 * TPW < CH) {
+        load_var(j + 2 * TPW, ra);
+        load_slots(j + 2 * TPW, ra);
+      }
+      if (j + TPW < CH) {
+        process(j + TPW, rb);
+        if (j + 3 * TPW < CH) {
+          load_var(j + 3 * TPW, rb);
+          load_slots(j + 3 * TPW, rb);
+        }
+      }
     }
   } else {
-    Regs ra;
 #pragma unroll 1
     for (int j = 0; j < CH; j += TPW) {
-      load(j, ra);
+      if (j > 0) {
+        load_var(j, ra);
+        load_slots(j, ra);
+      }
       process(j, ra);
     }
   }
@@ -309,11 +338,24 @@ __global__ void __launch_bounds__(256) k_pair_step(const PairArgs a) {
     a.g_out[t] = 0.f;
   }
 
+  // ---- one (loss, l2) partial per block, fixed order => deterministic
+  __shared__ float sred[8][2];
   loss_acc = orx_group_sum<32>(loss_acc);
   l2_acc = orx_group_sum<32>(l2_acc);
   if (lane == 0) {
-    a.partials[2 * warp] = loss_acc;
-    a.partials[2 * warp + 1] = l2_acc;
+    sred[threadIdx.x >> 5][0] = loss_acc;
+    sred[threadIdx.x >> 5][1] = l2_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, q = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      l += sred[w][0];
+      q += sred[w][1];
+    }
+    a.partials[2 * blockIdx.x] = l;
+    a.partials[2 * blockIdx.x + 1] = q;
   }
 }
 
@@ -433,11 +475,22 @@ __global__ void __launch_bounds__(256) k_pair_step_generic(const PairArgs a) {
       if (a.g_out) a.g_out[t] = g;
     }
   }
+  __shared__ float sred[8][2];
   loss_acc = orx_group_sum<32>(loss_acc);
   l2_acc = orx_group_sum<32>(l2_acc);
   if (lane == 0) {
-    a.partials[2 * warp] = loss_acc;
-    a.partials[2 * warp + 1] = l2_acc;
+    sred[threadIdx.x >> 5][0] = loss_acc;
+    sred[threadIdx.x >> 5][1] = l2_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, q = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      l += sred[w][0];
+      q += sred[w][1];
+    }
+    a.partials[2 * blockIdx.x] = l;
+    a.partials[2 * blockIdx.x + 1] = q;
   }
 }
 
@@ -489,14 +542,29 @@ __global__ void __launch_bounds__(256) k_sparse_tail(const TailArgs a) {
     float* W = (is_u ? a.U : a.I) + (int64_t)id * D;
     float* P0 = (is_u ? a.Us0 : a.Is0) + (int64_t)id * D;
     float* P1 = (is_u ? a.Us1 : a.Is1) + (int64_t)id * D;
-    for (int e = lane; e < D; e += 32) {
-      if (!ZERO_ONLY) {
-        float s0v = S0 ? P0[e] : 0.f, s1v = S1 ? P1[e] : 0.f;
-        W[e] = orx_apply<OPT>(W[e], G[e], s0v, s1v, a.opt);
-        if (S0) P0[e] = s0v;
-        if (S1) P1[e] = s1v;
+    if ((D & 3) == 0) {  // 128-bit path
+      for (int e = lane * 4; e < D; e += 128) {
+        const float4 g = *reinterpret_cast<const float4*>(G + e);
+        if (!ZERO_ONLY) {
+          float4 w = *reinterpret_cast<const float4*>(W + e);
+          float4 s0v = S0 ? *reinterpret_cast<const float4*>(P0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 s1v = S1 ? *reinterpret_cast<const float4*>(P1 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(W + e) = orx_apply4<OPT>(w, g, s0v, s1v, a.opt);
+          if (S0) *reinterpret_cast<float4*>(P0 + e) = s0v;
+          if (S1) *reinterpret_cast<float4*>(P1 + e) = s1v;
+        }
+        *reinterpret_cast<float4*>(G + e) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      G[e] = 0.f;
+    } else {
+      for (int e = lane; e < D; e += 32) {
+        if (!ZERO_ONLY) {
+          float s0v = S0 ? P0[e] : 0.f, s1v = S1 ? P1[e] : 0.f;
+          W[e] = orx_apply<OPT>(W[e], G[e], s0v, s1v, a.opt);
+          if (S0) P0[e] = s0v;
+          if (S1) P1[e] = s1v;
+        }
+        G[e] = 0.f;
+      }
     }
     if (!is_u && lane == 0) {
       if (!ZERO_ONLY) {
@@ -597,21 +665,41 @@ int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t ro
 // ---------------------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------------------
+// Tuning variants of the D=128 kernel, selected with ORX_PAIR_VARIANT (A/B on the GPU):
+//   0 (default): 2 CTAs/SM, register double-buffer   1: 3 CTAs/SM, double-buffer
+//   2: 4 CTAs/SM, single buffer                      3: 3 CTAs/SM, single buffer
+static int pair_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ORX_PAIR_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 template <int KIND, int OPT>
 static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaStream_t st, int* n_partials) {
   const int B = pa.B;
+  constexpr bool LAZY = (OPT == ORX_OPT_ADAM_LAZY);  // 9 rows per triplet: no register double-buffer
   auto go = [&](auto kern, int ch) {
     const int nw = (B + ch - 1) / ch;
     const int blocks = (nw + 7) / 8;
-    *n_partials = blocks * 8;
+    *n_partials = blocks;
     kern<<<blocks, 256, 0, st>>>(pa);
   };
   (void)n_warps_hint;
   switch (pa.D) {
-    case 32: go(k_pair_step<KIND, OPT, 32, 8>, 8); break;
-    case 64: go(k_pair_step<KIND, OPT, 64, 8>, 8); break;
-    case 128: go(k_pair_step<KIND, OPT, 128, 8>, 8); break;
-    case 256: go(k_pair_step<KIND, OPT, 256, 8>, 8); break;
+    case 32: go(k_pair_step<KIND, OPT, 32, 8, 2, !LAZY>, 8); break;
+    case 64: go(k_pair_step<KIND, OPT, 64, 8, 2, !LAZY>, 8); break;
+    case 128:
+      switch (LAZY ? 0 : pair_variant()) {
+        case 1: go(k_pair_step<KIND, OPT, 128, 8, 3, !LAZY>, 8); break;
+        case 2: go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8); break;
+        case 3: go(k_pair_step<KIND, OPT, 128, 8, 3, false>, 8); break;
+        default: go(k_pair_step<KIND, OPT, 128, 8, 2, !LAZY>, 8); break;
+      }
+      break;
+    case 256: go(k_pair_step<KIND, OPT, 256, 8, 2, !LAZY>, 8); break;
     default: go(k_pair_step_generic<KIND, OPT>, 8); break;
   }
   ORX_LAUNCH_CHECK();
@@ -670,7 +758,7 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
   pa.opt = orx_opt_to_dev(opt);
   pa.hu = c->hu; pa.hi = c->hi; pa.gu = c->gu; pa.gi = c->gi; pa.gb = c->gb;
   pa.partials = c->partials; pa.g_out = nullptr;
-  if ((rc = orx_ensure_partials(c, (B + 7) / 8 + 8, st))) return rc;
+  if ((rc = orx_ensure_partials(c, (B + 63) / 64 + 8, st))) return rc;
   pa.partials = c->partials;
   int n_partials = 0;
   rc = (kind == ORX_PAIR_BPR) ? launch_pair_step_kind<ORX_PAIR_BPR>(pa, opt->kind, st, &n_partials)
@@ -742,6 +830,7 @@ struct PairGradArgs {
   float margin, c_loss, c_l2, inv_B;
   float *d_user, *d_pos, *d_neg, *d_bp, *d_bn, *g_out;
   float* partials;
+  int slots;  // 1: outputs are indexed by the lookup's row (compact sharded form) instead of by triplet
 };
 
 template <int KIND>
@@ -799,16 +888,31 @@ __global__ void __launch_bounds__(256) k_pair_fwd_grad(const PairGradArgs a) {
             gn = t2 * (u - n) + c2 * n;
           }
         }
-        const int64_t o = (int64_t)t * D + d;
-        if (a.d_user) a.d_user[o] = gu;
-        if (a.d_pos) a.d_pos[o] = gp;
-        if (a.d_neg) a.d_neg[o] = gn;
+        if (a.slots) {
+          if (ok) {
+            a.d_user[(int64_t)uu * D + d] = gu;
+            a.d_pos[(int64_t)pp * D + d] = gp;
+            a.d_neg[(int64_t)nn * D + d] = gn;
+          }
+        } else {
+          const int64_t o = (int64_t)t * D + d;
+          if (a.d_user) a.d_user[o] = gu;
+          if (a.d_pos) a.d_pos[o] = gp;
+          if (a.d_neg) a.d_neg[o] = gn;
+        }
       }
     }
     if (lane == 0) {
       const float gbias = (KIND == ORX_PAIR_BPR) ? g : -g;
-      if (a.d_bp) a.d_bp[t] = gbias;
-      if (a.d_bn) a.d_bn[t] = -gbias;
+      if (a.slots) {
+        if (ok) {
+          a.d_bp[pp] = gbias;
+          a.d_bn[nn] = -gbias;
+        }
+      } else {
+        if (a.d_bp) a.d_bp[t] = gbias;
+        if (a.d_bn) a.d_bn[t] = -gbias;
+      }
       if (a.g_out) a.g_out[t] = g;
     }
   }
@@ -877,7 +981,7 @@ static int pair_fwd_grad(orx_ctx* c, int kind, const orx_table_t* user, const or
   a.uid = uid; a.pid = pid; a.nid = nid; a.B = B;
   a.margin = margin; a.c_loss = c_loss; a.c_l2 = c_l2; a.inv_B = 1.0f / (float)B;
   a.d_user = d_user; a.d_pos = d_pos; a.d_neg = d_neg; a.d_bp = d_bp; a.d_bn = d_bn; a.g_out = g_out;
-  a.partials = c->partials;
+  a.partials = c->partials; a.slots = 0;
   if (kind == ORX_PAIR_BPR) k_pair_fwd_grad<ORX_PAIR_BPR><<<blocks, 256, 0, st>>>(a);
   else k_pair_fwd_grad<ORX_PAIR_UCML><<<blocks, 256, 0, st>>>(a);
   ORX_LAUNCH_CHECK();
@@ -904,4 +1008,31 @@ extern "C" int orx_pairwise_grad(orx_handle_t h, int32_t kind, const orx_table_t
   ORX_CUDA(cudaSetDevice(h->device));
   return pair_fwd_grad(h, kind, user, item, item_bias, uid, pid, nid, B, margin, c_loss, c_l2, d_user, d_pos, d_neg,
                        d_bp, d_bn, g_out, nullptr, (cudaStream_t)s);
+}
+
+extern "C" int orx_pairwise_grad_slots(orx_handle_t h, int32_t kind, const float* user_rows, const float* item_rows,
+                                       const float* bias_rows, int32_t dim, const int32_t* uslot, const int32_t* pslot,
+                                       const int32_t* nslot, int32_t B, float margin, float c_loss, float c_l2,
+                                       float inv_B, float* d_user_rows, float* d_item_rows, float* d_bias_rows,
+                                       float* out4, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && user_rows && item_rows && bias_rows && uslot && pslot && nslot, "null input");
+  ORX_REQUIRE(d_user_rows && d_item_rows && d_bias_rows && out4, "null output");
+  ORX_REQUIRE(kind == ORX_PAIR_BPR || kind == ORX_PAIR_UCML, "unknown pairwise kind");
+  ORX_REQUIRE(B > 0 && dim > 0, "bad sizes");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)s;
+  const int nw = (B + 7) / 8, blocks = (nw + 7) / 8;
+  int rc = orx_ensure_partials(h, blocks * 8, st);
+  if (rc) return rc;
+  PairGradArgs a;
+  a.U = user_rows; a.I = item_rows; a.Bv = bias_rows;
+  a.rowsU = B; a.rowsI = 2 * (int64_t)B; a.D = dim;
+  a.uid = uslot; a.pid = pslot; a.nid = nslot; a.B = B;
+  a.margin = margin; a.c_loss = c_loss; a.c_l2 = c_l2; a.inv_B = inv_B;
+  a.d_user = d_user_rows; a.d_pos = d_item_rows; a.d_neg = d_item_rows; a.d_bp = d_bias_rows; a.d_bn = d_bias_rows;
+  a.g_out = nullptr; a.partials = h->partials; a.slots = 1;
+  if (kind == ORX_PAIR_BPR) k_pair_fwd_grad<ORX_PAIR_BPR><<<blocks, 256, 0, st>>>(a);
+  else k_pair_fwd_grad<ORX_PAIR_UCML><<<blocks, 256, 0, st>>>(a);
+  ORX_LAUNCH_CHECK();
+  return orx_launch_reduce_partials(h->partials, blocks * 8, kind == ORX_PAIR_BPR ? inv_B : 1.f, out4, st);
 }

@@ -1,0 +1,182 @@
+// orx_sharded.cu -- building blocks of the row-sharded (multi-GPU) step and of un-fused sparse applies:
+//   * orx_owner_bucket : counting-sort the lookups of a batch by owner rank (row r lives on rank r % R,
+//                        local row r / R) -> send order, per-owner counts, inverse permutation ("K9" bucket half)
+//   * orx_sparse_apply : Keras OptimizerV2 sparse apply of IndexedSlices (ids[n], values[n,D]) to one table:
+//                        dedup by row (batch hash), rows hit once are updated straight from their value row,
+//                        duplicated rows are summed in the staging buffer and updated once ("K8").
+// The reference has no multi-device code; the partitioning follows SURVEY 8(e).
+#include "orx_common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// owner bucketing: three tiny kernels (histogram, single-block scan, scatter)
+// ---------------------------------------------------------------------------------------
+__global__ void k_owner_hist(const int32_t* __restrict__ ids, int n, int R, int32_t* counts) {
+  extern __shared__ int32_t sh[];
+  for (int r = threadIdx.x; r < R; r += blockDim.x) sh[r] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int32_t id = ids[i];
+    atomicAdd(&sh[id >= 0 ? id % R : 0], 1);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x)
+    if (sh[r]) atomicAdd(counts + r, sh[r]);
+}
+
+__global__ void k_owner_scan(const int32_t* counts, int R, int32_t* cursor) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < R; ++r) {
+      cursor[r] = acc;
+      acc += counts[r];
+    }
+  }
+}
+
+// slot[i] = position of lookup i in the owner-sorted send order; send_local[slot] = local row on the owner
+__global__ void k_owner_scatter(const int32_t* __restrict__ ids, int n, int R, int32_t* cursor,
+                                int32_t* __restrict__ send_local, int32_t* __restrict__ slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t id = ids[i];
+  const int r = id >= 0 ? id % R : 0;
+  const int s = atomicAdd(cursor + r, 1);
+  send_local[s] = id >= 0 ? id / R : -1;
+  slot[i] = s;
+}
+
+extern "C" int orx_owner_bucket(orx_handle_t h, const int32_t* ids, int32_t n, int32_t world, int32_t* counts,
+                                int32_t* send_local, int32_t* slot, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && ids && counts && send_local && slot, "null pointer");
+  ORX_REQUIRE(n >= 0 && world >= 1 && world <= 1024, "bad sizes");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)s;
+  ORX_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * world, st));
+  if (n == 0) return ORX_OK;
+  int32_t* cursor = h->counters + 4;  // needs `world` ints: reuse a dedicated scratch
+  if (world > 4) {
+    if (!h->bucket_cursor) ORX_CUDA(cudaMalloc(&h->bucket_cursor, sizeof(int32_t) * 1024));
+    cursor = h->bucket_cursor;
+  }
+  int blocks = (n + 255) / 256;
+  if (blocks > h->num_sms * 4) blocks = h->num_sms * 4;
+  k_owner_hist<<<blocks, 256, sizeof(int32_t) * world, st>>>(ids, n, world, counts);
+  ORX_LAUNCH_CHECK();
+  k_owner_scan<<<1, 32, 0, st>>>(counts, world, cursor);
+  ORX_LAUNCH_CHECK();
+  k_owner_scatter<<<(n + 255) / 256, 256, 0, st>>>(ids, n, world, cursor, send_local, slot);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// generic sparse apply
+// ---------------------------------------------------------------------------------------
+template <int OPT>
+__global__ void __launch_bounds__(256) k_sparse_apply(float* var, float* s0, float* s1, int64_t rows, int D,
+                                                      const int32_t* __restrict__ ids,
+                                                      const float* __restrict__ vals, int n, OrxHash hsh,
+                                                      float* gstage, OrxOptDev o) {
+  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool STAGE_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= n) return;
+  const int32_t id = ids[b];
+  if (id < 0 || (int64_t)id >= rows) return;
+  int d = -1;
+  uint32_t c = 0;
+  if (lane == 0) c = orx_hash_find(hsh, id, &d);
+  c = __shfl_sync(ORX_FULL, c, 0);
+  d = __shfl_sync(ORX_FULL, d, 0);
+  const float* v = vals + (int64_t)b * D;
+  if (!STAGE_ONLY && c == 1u) {
+    float* w = var + (int64_t)id * D;
+    for (int e = lane; e < D; e += 32) {
+      const int64_t off = (int64_t)id * D + e;
+      float a = S0 ? s0[off] : 0.f, bb = S1 ? s1[off] : 0.f;
+      w[e] = orx_apply<OPT>(w[e], v[e], a, bb, o);
+      if (S0) s0[off] = a;
+      if (S1) s1[off] = bb;
+    }
+  } else {
+    for (int e = lane; e < D; e += 32) atomicAdd(gstage + (int64_t)d * D + e, v[e]);
+  }
+}
+
+// tail for one table: staged rows -> optimizer, staging zeroed, hash cleared, counters reset
+template <int OPT>
+__global__ void __launch_bounds__(256) k_sparse_apply_tail(float* var, float* s0, float* s1, int D, OrxHash hsh,
+                                                           float* gstage, OrxOptDev o, int32_t* counters) {
+  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool ZERO_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int ns = *hsh.counter;
+  for (int r = gwarp; r < ns; r += nwarps) {
+    const int id = hsh.did[r];
+    for (int e = lane; e < D; e += 32) {
+      const int64_t off = (int64_t)id * D + e;
+      if (!ZERO_ONLY) {
+        float a = S0 ? s0[off] : 0.f, bb = S1 ? s1[off] : 0.f;
+        var[off] = orx_apply<OPT>(var[off], gstage[(int64_t)r * D + e], a, bb, o);
+        if (S0) s0[off] = a;
+        if (S1) s1[off] = bb;
+      }
+      gstage[(int64_t)r * D + e] = 0.f;
+    }
+  }
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (uint32_t i = tid; i <= hsh.mask; i += nth) hsh.slots[i] = 0ull;
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(counters + 2, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 4) counters[threadIdx.x] = 0;
+}
+
+extern "C" int orx_sparse_apply(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
+                                int32_t n, const orx_opt_t* opt, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && tab && tab->var && opt, "null pointer");
+  ORX_REQUIRE(n >= 0 && tab->rows > 0 && tab->dim > 0, "bad sizes");
+  ORX_REQUIRE(opt->kind >= ORX_OPT_SGD && opt->kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
+  if (opt->kind != ORX_OPT_SGD) ORX_REQUIRE(tab->s0, "optimizer slot s0 missing");
+  if (opt->kind >= ORX_OPT_ADAM_LAZY) ORX_REQUIRE(tab->s1, "optimizer slot s1 missing");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)s;
+  const bool dense = opt->kind == ORX_OPT_ADAM_DENSE;
+  if (n == 0 && !dense) return ORX_OK;
+  ORX_REQUIRE(n == 0 || (ids && values), "null ids/values");
+  const int D = tab->dim;
+  int rc = orx_ensure_workspace(h, n > 0 ? n : 1, D, dense);
+  if (rc) return rc;
+  const OrxOptDev o = orx_opt_to_dev(opt);
+  // the user-side hash / staging pair serves as "the" table here
+  if (n > 0) {
+    if ((rc = orx_launch_index_build(h, ids, tab->rows, n, nullptr, nullptr, 1, 0, dense, st))) return rc;
+    const int blocks = (n + 7) / 8;
+    switch (opt->kind) {
+      case ORX_OPT_SGD: k_sparse_apply<ORX_OPT_SGD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, values, n, h->hu, h->gu, o); break;
+      case ORX_OPT_ADAGRAD: k_sparse_apply<ORX_OPT_ADAGRAD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, values, n, h->hu, h->gu, o); break;
+      case ORX_OPT_ADAM_LAZY: k_sparse_apply<ORX_OPT_ADAM_LAZY><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, values, n, h->hu, h->gu, o); break;
+      default: k_sparse_apply<ORX_OPT_ADAM_DENSE><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, values, n, h->hu, h->gu, o); break;
+    }
+    ORX_LAUNCH_CHECK();
+  }
+  if (dense)
+    if ((rc = orx_launch_adam_sweep(h, tab->var, tab->s0, tab->s1, tab->rows, D, h->hu, h->gu, o, st))) return rc;
+  const int grid = h->num_sms * 2;
+  switch (opt->kind) {
+    case ORX_OPT_SGD: k_sparse_apply_tail<ORX_OPT_SGD><<<grid, 256, 0, st>>>(tab->var, tab->s0, tab->s1, D, h->hu, h->gu, o, h->counters); break;
+    case ORX_OPT_ADAGRAD: k_sparse_apply_tail<ORX_OPT_ADAGRAD><<<grid, 256, 0, st>>>(tab->var, tab->s0, tab->s1, D, h->hu, h->gu, o, h->counters); break;
+    case ORX_OPT_ADAM_LAZY: k_sparse_apply_tail<ORX_OPT_ADAM_LAZY><<<grid, 256, 0, st>>>(tab->var, tab->s0, tab->s1, D, h->hu, h->gu, o, h->counters); break;
+    default: k_sparse_apply_tail<ORX_OPT_ADAM_DENSE><<<grid, 256, 0, st>>>(tab->var, tab->s0, tab->s1, D, h->hu, h->gu, o, h->counters); break;
+  }
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}

@@ -70,6 +70,9 @@ class Engine:
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    make_table = staticmethod(table)
+    make_opt = staticmethod(opt)
+
     # ---- measurement hook ----
     def profile_enable(self, on=True):
         _lib.check(self.lib.orx_profile_enable(self.h, 1 if on else 0))
@@ -125,6 +128,30 @@ class Engine:
                                               _ptr(pid), _ptr(nid), uid.numel(), margin, c_loss, c_l2, _ptr(d_user),
                                               _ptr(d_pos), _ptr(d_neg), _ptr(d_bp), _ptr(d_bn), _ptr(g_out),
                                               self.stream()), "orx_pairwise_grad")
+
+    def pairwise_grad_slots(self, kind, user_rows, item_rows, bias_rows, uslot, pslot, nslot, inv_B, d_user, d_item,
+                            d_bias, out4, margin=0.5, c_loss=1.0, c_l2=1.0):
+        _lib.check(self.lib.orx_pairwise_grad_slots(self.h, kind, _ptr(user_rows), _ptr(item_rows), _ptr(bias_rows),
+                                                    user_rows.shape[1], _ptr(uslot), _ptr(pslot), _ptr(nslot),
+                                                    uslot.numel(), margin, c_loss, c_l2, inv_B, _ptr(d_user),
+                                                    _ptr(d_item), _ptr(d_bias), _ptr(out4), self.stream()),
+                   "orx_pairwise_grad_slots")
+
+    # ---- un-fused sparse apply / multi-GPU building blocks ------------------------------
+    def sparse_apply(self, tab, ids, values, o):
+        n = 0 if ids is None else ids.numel()
+        _lib.check(self.lib.orx_sparse_apply(self.h, C.byref(tab), _ptr(ids), _ptr(values), n, C.byref(o),
+                                             self.stream()), "orx_sparse_apply")
+
+    def owner_bucket(self, ids, world):
+        """-> (counts[world], send_local[n], slot[n]) device int32 tensors."""
+        n = ids.numel()
+        counts = torch.empty(world, dtype=torch.int32, device=ids.device)
+        send_local = torch.empty(n, dtype=torch.int32, device=ids.device)
+        slot = torch.empty(n, dtype=torch.int32, device=ids.device)
+        _lib.check(self.lib.orx_owner_bucket(self.h, _ptr(ids), n, world, _ptr(counts), _ptr(send_local), _ptr(slot),
+                                             self.stream()), "orx_owner_bucket")
+        return counts, send_local, slot
 
     # ---- pointwise ---------------------------------------------------------------------
     def pointwise_step(self, kind, user, item, bias, w, uid, iid, label, o, out4, a=1.0, b=1.0, use_sigmoid=False,

@@ -5,6 +5,7 @@ The step protocol (tf2_examples/bpr_citeulike.py:33-39) is executed as ONE libor
 openrec_b200/tfshim/core.py."""
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from ... import native as N
@@ -16,6 +17,45 @@ from ...tfshim.keras import Model
 def ids_of(x):
     """int32 device ids from whatever the caller feeds (Keras Embedding casts to int32)."""
     return N.ids32(convert(x).t)
+
+
+def ids_any(x):
+    """-> (int32 ids, on_host).  Host data (numpy / CPU tensors) stays on the host in pinned memory so the
+    fused step can take it through the C-ABI's host-buffer entry point (one call: H2D + kernels + D2H)."""
+    from ...tfshim import core
+    if isinstance(x, (core.Tensor, core.Variable)):
+        t = x.t
+    elif torch.is_tensor(x):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+    if t.is_cuda or core.device().type != "cuda":
+        return N.ids32(t), False
+    t = t.reshape(-1)
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    t = t.contiguous()
+    return (t if t.is_pinned() else t.pin_memory()), True
+
+
+class _OutRing:
+    """Pinned float[4] result buffers + events, recycled; a buffer still owned by an unread step node is
+    resolved (event wait + copy to python floats) before reuse."""
+
+    def __init__(self, n=32):
+        self.bufs = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(n)]
+        self.events = [torch.cuda.Event() for _ in range(n)]
+        self.owner = [None] * n
+        self.i = 0
+
+    def take(self, node):
+        k = self.i
+        self.i = (k + 1) % len(self.bufs)
+        old = self.owner[k]
+        if old is not None and old.out_host is self.bufs[k]:
+            old.host_values()
+        self.owner[k] = node
+        return self.bufs[k], self.events[k]
 
 
 class FusedRecommender(Model):
@@ -30,12 +70,26 @@ class FusedRecommender(Model):
     def _orx_step_variables(self):
         return self.trainable_variables
 
-    def _new_node(self, *ids):
+    def _new_node(self, *ids, host_ids=None):
         if self.user_latent_factor.output_dim != self.item_latent_factor.output_dim:
             raise ValueError("user and item embedding dims must match (the reference multiplies them elementwise)")
         node = StepNode(self, 2)
-        node.ids = ids
+        node.ids = ids if ids else None
+        node.host_ids = host_ids
         return node, LazyScalar(node, {0: 1.0}), LazyScalar(node, {1: 1.0})
+
+    def _device_ids(self, node):
+        """ids on the device (staged from pinned host memory on first use)."""
+        if node.ids is None:
+            dev = self.user_latent_factor.embeddings.t.device
+            node.ids = tuple(t.to(dev, non_blocking=True) for t in node.host_ids)
+        return node.ids
+
+    def _out_ring(self):
+        ring = getattr(self, "_orx_ring", None)
+        if ring is None:
+            ring = self._orx_ring = _OutRing()
+        return ring
 
     def _orx_apply(self, node, grads_and_vars, optimizer):
         if node.stepped:
@@ -48,10 +102,15 @@ class FusedRecommender(Model):
                 "apply_gradients: the fused step needs the gradients of ALL of the model's trainable variables "
                 "w.r.t. one objective (as tape.gradient(loss, model.trainable_variables) returns them)")
         c_loss, c_l2 = float(coefs[0].get(0, 0.0)), float(coefs[0].get(1, 0.0))
-        if node.out is None:
-            node.out = torch.zeros(4, dtype=torch.float32, device=node.ids[0].device)
-        self._orx_run_step(node, optimizer, c_loss, c_l2)
+        if node.host_ids is not None and hasattr(self, "_orx_run_step_host"):
+            node.out = None
+            self._orx_run_step_host(node, optimizer, c_loss, c_l2)
+        else:
+            if node.out is None:
+                node.out = torch.zeros(4, dtype=torch.float32, device=self._device_ids(node)[0].device)
+            self._orx_run_step(node, optimizer, c_loss, c_l2)
         node.stepped = True
+        node.ids = node.host_ids = None   # the batch is consumed; keep unread loss handles light
 
     def _orx_materialize_grad(self, node, var, coef):
         """IndexedSlices (indices, values) of d(objective)/d(var), not deduplicated (TF form)."""

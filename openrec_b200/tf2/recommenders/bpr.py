@@ -4,7 +4,7 @@ import torch
 from ... import native as N
 from ...tfshim.core import Tensor
 from ..modules import LatentFactor, PairwiseLogLoss
-from ._base import FusedRecommender, ids_of
+from ._base import FusedRecommender, ids_any, ids_of
 
 
 class BPR(FusedRecommender):
@@ -25,19 +25,33 @@ class BPR(FusedRecommender):
 
     def call(self, user_id, p_item_id, n_item_id):
         """-> (loss, l2_loss) as lazy scalars (bpr.py:21-37)."""
-        _, loss, l2 = self._new_node(ids_of(user_id), ids_of(p_item_id), ids_of(n_item_id))
+        ids = [ids_any(x) for x in (user_id, p_item_id, n_item_id)]
+        if all(h for _, h in ids):     # host batch: stays in pinned memory until the fused step takes it
+            _, loss, l2 = self._new_node(host_ids=tuple(t for t, _ in ids))
+            return loss, l2
+        dev = self.user_latent_factor.embeddings.t.device
+        _, loss, l2 = self._new_node(*(t.to(dev, non_blocking=True) if h else t for t, h in ids))
         return loss, l2
 
     # ---- kernels behind the step protocol
     def _orx_forward(self, node):
-        N.engine().pairwise_fwd(self._kind, *self._tables(), *node.ids, node.out, self._get_margin())
+        N.engine().pairwise_fwd(self._kind, *self._tables(), *self._device_ids(node), node.out, self._get_margin())
 
     def _orx_run_step(self, node, optimizer, c_loss, c_l2):
-        N.engine().pairwise_step(self._kind, *self._tables(optimizer), *node.ids, optimizer.opt_struct(), node.out,
-                                 self._get_margin(), c_loss, c_l2)
+        N.engine().pairwise_step(self._kind, *self._tables(optimizer), *self._device_ids(node),
+                                 optimizer.opt_struct(), node.out, self._get_margin(), c_loss, c_l2)
+
+    def _orx_run_step_host(self, node, optimizer, c_loss, c_l2):
+        """ids in pinned host memory -> orx_pairwise_step_host: H2D, the three kernels and the D2H of
+        (loss, l2_loss) are one C call's worth of stream work; the result lands in a pinned buffer."""
+        buf, ev = self._out_ring().take(node)
+        N.engine().pairwise_step_host(self._kind, *self._tables(optimizer), *node.host_ids, optimizer.opt_struct(),
+                                      buf, self._get_margin(), c_loss, c_l2)
+        ev.record()
+        node.out_host, node.event = buf, ev
 
     def _orx_run_grad(self, node, var, c_loss, c_l2):
-        uid, pid, nid = node.ids
+        uid, pid, nid = self._device_ids(node)
         B, D = uid.numel(), self.user_latent_factor.output_dim
         dev = uid.device
         kw = {}

@@ -34,15 +34,15 @@ class WRMF(FusedRecommender):
 
     def _orx_forward(self, node):
         a, b, sig = self._point_params()
-        N.engine().pointwise_fwd(self._kind, *self._tables(), self._w(), *node.ids, node.out, a, b, sig)
+        N.engine().pointwise_fwd(self._kind, *self._tables(), self._w(), *self._device_ids(node), node.out, a, b, sig)
 
     def _orx_run_step(self, node, optimizer, c_loss, c_l2):
         a, b, sig = self._point_params()
-        N.engine().pointwise_step(self._kind, *self._tables(optimizer), self._w(optimizer), *node.ids,
+        N.engine().pointwise_step(self._kind, *self._tables(optimizer), self._w(optimizer), *self._device_ids(node),
                                   optimizer.opt_struct(), node.out, a, b, sig, c_loss, c_l2)
 
     def _orx_run_grad(self, node, var, c_loss, c_l2):
-        uid, iid, lab = node.ids
+        uid, iid, lab = self._device_ids(node)
         B, D = uid.numel(), self.user_latent_factor.output_dim
         dev = uid.device
         a, b, sig = self._point_params()

@@ -112,10 +112,11 @@ def convert(value, dtype=None, *, pin=True):
         t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
-    if not t.is_cuda:
-        if pin and t.numel() > 0:
+    dev = device()
+    if t.device != dev:
+        if pin and t.numel() > 0 and dev.type == "cuda" and not t.is_cuda:
             t = t.pin_memory()
-        t = t.to(device(), non_blocking=True)
+        t = t.to(dev, non_blocking=True)
     return Tensor(t)
 
 
@@ -187,11 +188,27 @@ class StepNode:
         self.out = None        # device float tensor [4] once a kernel has produced the values
         self.stepped = False   # the fused training step has run (tables already updated)
         self.tape = _tape_stack[-1] if _tape_stack else None
+        self.out_host = None   # pinned host float[4] + event when the step went through host buffers
+        self.event = None
+        self._vals = None      # resolved python floats
+
+    def host_values(self):
+        """Python floats of the outputs if the step wrote them to pinned host memory (waits for the
+        step's event), else None."""
+        if self._vals is None and self.out_host is not None:
+            self.event.synchronize()
+            self._vals = self.out_host.tolist()
+            self.out_host = self.event = None
+        return self._vals
 
     def ensure_forward(self):
         if self.out is None:
-            self.out = torch.zeros(4, dtype=torch.float32, device=device())
-            self.model._orx_forward(self)   # forward-only kernel fills out[0..n_outputs)
+            hv = self.host_values()
+            if hv is not None:
+                self.out = torch.tensor(hv, dtype=torch.float32, device=device())
+            else:
+                self.out = torch.zeros(4, dtype=torch.float32, device=device())
+                self.model._orx_forward(self)   # forward-only kernel fills out[0..n_outputs)
         return self.out
 
 
@@ -216,6 +233,9 @@ class LazyScalar:
         return Tensor(t)
 
     def numpy(self):
+        hv = self.node.host_values()
+        if hv is not None:   # loss already sits in pinned host memory: no device op, no extra sync
+            return np.float32(sum(c * hv[k] for k, c in self.coef.items()) + self.const)
         return self.value().numpy()
 
     def __float__(self):

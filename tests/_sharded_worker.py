@@ -1,0 +1,38 @@
+"""Worker of tests/test_sharded_gloo.py: one rank of a world_size-R gloo job on CPU."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    out_path, kind, opt_kind = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fake_engine import FakeEngine
+    from openrec_b200.sharded import ShardedPairwise
+    rng = np.random.default_rng(99)                       # same global problem on every rank
+    U, I, D, B = 61, 83, 16, 40
+    sc = 0.05 if kind == 0 else 0.4
+    user, item, bias = (rng.uniform(-sc, sc, s).astype(np.float32) for s in ((U, D), (I, D), (I, 1)))
+    m = ShardedPairwise(FakeEngine(), rank, world, U, I, D, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
+    m.load_global(user, item, bias)
+    losses = []
+    for step in range(3):
+        ids = [rng.integers(0, n, B * world).astype(np.int32) for n in (U, I, I)]   # global batch
+        mine = [torch.from_numpy(a[rank * B:(rank + 1) * B].copy()) for a in ids]
+        losses.append(m.step(*mine).numpy().copy())
+    full = [t.numpy() for t in m.gather_global()]
+    if rank == 0:
+        np.savez(out_path, user=full[0], item=full[1], bias=full[2], losses=np.stack(losses))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
