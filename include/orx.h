@@ -160,6 +160,11 @@ ORX_API int orx_pointwise_grad(orx_handle_t h, int32_t kind, const orx_table_t* 
  * an Embedding, tf2_examples/bpr_citeulike.py:37-38).  Used by owners in the row-sharded step and by DLRM. */
 ORX_API int orx_sparse_apply(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
                              int32_t n, const orx_opt_t* opt_host, orx_stream_t s);
+/* Same with strided inputs: id i = ids[i*id_stride], value row i = values + i*value_ld (DLRM: ids = sparse[:,k],
+ * values = dZ[:,k,:]). */
+ORX_API int orx_sparse_apply_strided(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
+                                     const float* values, int64_t value_ld, int32_t n, const orx_opt_t* opt_host,
+                                     orx_stream_t s);
 /* orx_owner_bucket: row r lives on rank r % world at local row r / world.  counts[world] = lookups per owner,
  * send_local[n] = local rows in owner-sorted send order, slot[n] = position of lookup i in that order. */
 ORX_API int orx_owner_bucket(orx_handle_t h, const int32_t* ids, int32_t n, int32_t world, int32_t* counts,
@@ -168,6 +173,36 @@ ORX_API int orx_owner_bucket(orx_handle_t h, const int32_t* ids, int32_t n, int3
 /* ---- dense variables (GMF w, MLP kernels/biases): Keras dense apply ---------------------- */
 ORX_API int orx_dense_apply(orx_handle_t h, float* var, float* s0, float* s1, const float* grad, int64_t n,
                     const orx_opt_t* opt_host, orx_stream_t s);
+
+/* ---- DLRM (recommenders/dlrm.py:63-100) ----------------------------------------------------------
+ * The model is composed on the host from these pieces, all with explicit leading dimensions so that the
+ * stacked feature tensor, the concat of (dense_vec, interactions) and their gradients are never copied.
+ * orx_gather_strided: one sparse feature's LatentFactor lookup, ids = sparse[:,k] (stride = #features),
+ *   out = Z[:,k,:]                                                                   (dlrm.py:83-85)
+ * orx_mlp_layer_fwd/bwd: one keras Dense(units, activation) of MLP (modules/multi_layer_perceptron.py:9-16),
+ *   kernel w[in,out], act 0 none / 1 relu / 2 sigmoid; bwd overwrites dy with dL/dz and produces dw, db, dx.
+ * orx_interact_fwd/bwd: SecondOrderFeatureInteraction over F features = F-1 embedding rows + the dense
+ *   vector as LAST feature (modules/second_order_feature_interaction.py:12-34, dlrm.py:89-92);
+ *   mode 0 = the reference's bug-compatible output, mode 1 = strictly-lower triangle of Z Z^T.
+ * orx_pred_loss: clip (dlrm.py:97-98) + keras MeanSquaredError (kind 0) / BinaryCrossentropy (kind 1)
+ *   (dlrm.py:52-55,72-73); out4[0] = loss, dpred = dloss/dpred. */
+ORX_API int orx_gather_strided(orx_handle_t h, const float* tab, int64_t rows, int32_t dim, const int32_t* ids,
+                               int64_t id_stride, int64_t n, float* out, int64_t out_ld, int32_t* n_bad,
+                               orx_stream_t s);
+ORX_API int orx_mlp_layer_fwd(orx_handle_t h, const float* x, int64_t ldx, int32_t B, int32_t in, const float* w,
+                              const float* bias, int32_t out, int32_t act, float* y, int64_t ldy, orx_stream_t s);
+ORX_API int orx_mlp_layer_bwd(orx_handle_t h, const float* x, int64_t ldx, const float* y, int64_t ldy, const float* w,
+                              int32_t B, int32_t in, int32_t out, int32_t act, float* dy, int64_t lddy, float* dx,
+                              int64_t lddx, float* dw, float* db, orx_stream_t s);
+ORX_API int orx_interact_fwd(orx_handle_t h, const float* emb, int64_t emb_ld, const float* dense, int64_t dense_ld,
+                             int32_t B, int32_t F, int32_t D, int32_t self_interaction, int32_t mode, float* out,
+                             int64_t out_ld, orx_stream_t s);
+ORX_API int orx_interact_bwd(orx_handle_t h, const float* emb, int64_t emb_ld, const float* dense, int64_t dense_ld,
+                             const float* dout, int64_t dout_ld, int32_t B, int32_t F, int32_t D,
+                             int32_t self_interaction, int32_t mode, float* demb, int64_t demb_ld, float* ddense,
+                             int64_t ddense_ld, orx_stream_t s);
+ORX_API int orx_pred_loss(orx_handle_t h, const float* pred, const float* label, int32_t B, int32_t kind,
+                          float clip_threshold, float* pred_out, float* dpred, float* out4, orx_stream_t s);
 
 /* ---- inference: full-catalogue scoring (bpr.py:39-43, wrmf.py:36-40, ucml.py:50-53, gmf.py:36-41)
  * scores[Bu, I] = user_rows . item^T + bias   (DOT; GMF passes user_rows pre-multiplied by w via `scale`)

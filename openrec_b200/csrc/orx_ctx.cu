@@ -51,7 +51,9 @@ static uint32_t pow2_at_least(int64_t n) {
 }
 
 static int alloc_hash(OrxHash& t, int64_t lookups, int32_t* counter) {
-  uint32_t cap = pow2_at_least(2 * lookups);
+  // load factor <= 0.25: with linear probing the slowest of a warp's 32 inserts/probes sets the pace
+  // (profile r1b: ~7 serialized L2 round trips per warp at 0.5)
+  uint32_t cap = pow2_at_least(4 * lookups);
   int lg = 0;
   while ((1u << lg) < cap) ++lg;
   t.mask = cap - 1;

@@ -1,0 +1,353 @@
+// orx_dlrm.cu -- DLRM building blocks (rows a11-a13): strided per-feature gather (K5), second-order
+// interaction fwd/bwd (K6), Dense layers fwd/bwd (K7, fp32 SIMT tiles -- 1e-5 parity first; the tcgen05
+// 3xTF32 path replaces the inner product later), prediction loss.
+//
+// Reference path: openrec/tf2/recommenders/dlrm.py:63-100, modules/multi_layer_perceptron.py:5-18,
+// modules/second_order_feature_interaction.py:12-34.
+#include "orx_common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// K5: out[b*out_ld + :D] = tab[ids[b*id_stride], :D]   (dlrm.py:83-85, one call per sparse feature)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_strided(const float* __restrict__ tab, int64_t rows, int D,
+                                                        const int32_t* __restrict__ ids, int64_t id_stride, int64_t n,
+                                                        float* __restrict__ out, int64_t out_ld, int32_t* n_bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec = ((D & 3) == 0) && ((out_ld & 3) == 0);
+  for (int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n; b += nw) {
+    const int64_t id = ids[b * id_stride];
+    const bool ok = id >= 0 && id < rows;
+    if (!ok && lane == 0 && n_bad) atomicAdd(n_bad, 1);
+    if (vec) {
+      const float4* src = reinterpret_cast<const float4*>(tab + id * D);
+      float4* dst = reinterpret_cast<float4*>(out + b * out_ld);
+      for (int e = lane; e < D / 4; e += 32) dst[e] = ok ? __ldg(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int e = lane; e < D; e += 32) out[b * out_ld + e] = ok ? __ldg(tab + id * D + e) : 0.f;
+    }
+  }
+}
+
+extern "C" int orx_gather_strided(orx_handle_t h, const float* tab, int64_t rows, int32_t dim, const int32_t* ids,
+                                  int64_t id_stride, int64_t n, float* out, int64_t out_ld, int32_t* n_bad,
+                                  orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && tab && ids && out, "null pointer");
+  ORX_REQUIRE(rows > 0 && dim > 0 && n >= 0 && id_stride >= 1 && out_ld >= dim, "bad sizes");
+  if (n == 0) return ORX_OK;
+  ORX_CUDA(cudaSetDevice(h->device));
+  int64_t blocks = (n + 7) / 8;
+  if (blocks > (int64_t)h->num_sms * 32) blocks = (int64_t)h->num_sms * 32;
+  k_gather_strided<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(tab, rows, dim, ids, id_stride, n, out, out_ld, n_bad);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K6: second-order interaction.  Features: F-1 embedding rows emb[b, f, :] (row stride emb_ld per
+// feature, F-1 of them contiguous per sample) + the dense vector dense[b*dense_ld + :] as LAST feature
+// (dlrm.py:89-92: sparse_emb_vecs + [dense_emb_vec]).
+//   mode 0 (reference, bug-compatible): out = row-major entries (i,j>=i [j>i if !self]) of
+//           lower_tri(Z Z^T)  => only the diagonal survives;
+//   mode 1 (dlrm): row-major entries (i, j<i [j<=i if self]) of Z Z^T.
+// ---------------------------------------------------------------------------------------
+#define ORX_MAX_F 64
+
+__device__ __forceinline__ bool inter_selected(int mode, int self, int i, int j) {
+  return mode == 0 ? (self ? j >= i : j > i) : (self ? j <= i : j < i);
+}
+
+__global__ void __launch_bounds__(128) k_interact_fwd(const float* __restrict__ emb, int64_t emb_ld,
+                                                      const float* __restrict__ dense, int64_t dense_ld, int B, int F,
+                                                      int D, int self, int mode, float* __restrict__ out,
+                                                      int64_t out_ld) {
+  extern __shared__ float sz[];  // [F][D+1]
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const int Dp = D + 1;
+  for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
+    const int f = e / D, d = e % D;
+    sz[f * Dp + d] = f < F - 1 ? emb[(int64_t)b * emb_ld + (int64_t)f * D + d] : dense[(int64_t)b * dense_ld + d];
+  }
+  __syncthreads();
+  // enumerate the selected (i,j) pairs row-major; thread t takes pairs t, t+blockDim, ...
+  int q = 0;
+  for (int i = 0; i < F; ++i)
+    for (int j = 0; j < F; ++j) {
+      if (!inter_selected(mode, self, i, j)) continue;
+      if ((q % blockDim.x) == threadIdx.x) {
+        float acc = 0.f;
+        if (mode == 1 || j == i) {  // mode 0: lower_tri(P)[i,j] with j>=i is non-zero only on the diagonal
+          for (int d = 0; d < D; ++d) acc += sz[i * Dp + d] * sz[j * Dp + d];
+        }
+        out[(int64_t)b * out_ld + q] = acc;
+      }
+      ++q;
+    }
+}
+
+// dZ = (dP + dP^T) Z restricted to the selected entries; emb part -> demb[b,f,:], dense part ADDED to ddense.
+__global__ void __launch_bounds__(128) k_interact_bwd(const float* __restrict__ emb, int64_t emb_ld,
+                                                      const float* __restrict__ dense, int64_t dense_ld,
+                                                      const float* __restrict__ dout, int64_t dout_ld, int B, int F,
+                                                      int D, int self, int mode, float* __restrict__ demb,
+                                                      int64_t demb_ld, float* __restrict__ ddense,
+                                                      int64_t ddense_ld) {
+  extern __shared__ float sm[];  // Z [F][D+1] then dP [F][F]
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const int Dp = D + 1;
+  float* sz = sm;
+  float* sp = sm + F * Dp;
+  for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
+    const int f = e / D, d = e % D;
+    sz[f * Dp + d] = f < F - 1 ? emb[(int64_t)b * emb_ld + (int64_t)f * D + d] : dense[(int64_t)b * dense_ld + d];
+  }
+  for (int e = threadIdx.x; e < F * F; e += blockDim.x) sp[e] = 0.f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int q = 0;
+    for (int i = 0; i < F; ++i)
+      for (int j = 0; j < F; ++j) {
+        if (!inter_selected(mode, self, i, j)) continue;
+        if (mode == 1 || j == i) sp[i * F + j] = dout[(int64_t)b * dout_ld + q];
+        ++q;
+      }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
+    const int i = e / D, d = e % D;
+    float acc = 0.f;
+    for (int j = 0; j < F; ++j) acc += (sp[i * F + j] + sp[j * F + i]) * sz[j * Dp + d];
+    if (i < F - 1) demb[(int64_t)b * demb_ld + (int64_t)i * D + d] = acc;
+    else ddense[(int64_t)b * ddense_ld + d] += acc;
+  }
+}
+
+extern "C" int orx_interact_fwd(orx_handle_t h, const float* emb, int64_t emb_ld, const float* dense,
+                                int64_t dense_ld, int32_t B, int32_t F, int32_t D, int32_t self_interaction,
+                                int32_t mode, float* out, int64_t out_ld, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && dense && out && (F == 1 || emb), "null pointer");
+  ORX_REQUIRE(B >= 0 && F >= 1 && F <= ORX_MAX_F && D > 0 && (mode == 0 || mode == 1), "bad sizes/mode");
+  if (B == 0) return ORX_OK;
+  ORX_CUDA(cudaSetDevice(h->device));
+  const size_t smem = sizeof(float) * (size_t)F * (D + 1);
+  ORX_REQUIRE(smem <= 200 * 1024, "F*D too large for the interaction kernel");
+  if (smem > 48 * 1024) ORX_CUDA(cudaFuncSetAttribute(k_interact_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_interact_fwd<<<B, 128, smem, (cudaStream_t)s>>>(emb, emb_ld, dense, dense_ld, B, F, D, self_interaction, mode, out, out_ld);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+extern "C" int orx_interact_bwd(orx_handle_t h, const float* emb, int64_t emb_ld, const float* dense,
+                                int64_t dense_ld, const float* dout, int64_t dout_ld, int32_t B, int32_t F, int32_t D,
+                                int32_t self_interaction, int32_t mode, float* demb, int64_t demb_ld, float* ddense,
+                                int64_t ddense_ld, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && dense && dout && ddense && (F == 1 || (emb && demb)), "null pointer");
+  ORX_REQUIRE(B >= 0 && F >= 1 && F <= ORX_MAX_F && D > 0 && (mode == 0 || mode == 1), "bad sizes/mode");
+  if (B == 0) return ORX_OK;
+  ORX_CUDA(cudaSetDevice(h->device));
+  const size_t smem = sizeof(float) * ((size_t)F * (D + 1) + (size_t)F * F);
+  ORX_REQUIRE(smem <= 200 * 1024, "F*D too large for the interaction kernel");
+  if (smem > 48 * 1024) ORX_CUDA(cudaFuncSetAttribute(k_interact_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_interact_bwd<<<B, 128, smem, (cudaStream_t)s>>>(emb, emb_ld, dense, dense_ld, dout, dout_ld, B, F, D, self_interaction, mode, demb, demb_ld, ddense, ddense_ld);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K7: Dense layers.  One fp32 SIMT GEMM  C[M,N] (+)= op(A)[M,K] * op(B)[K,N]  with 64x64x16 tiles and
+// a 4x4 register block per thread; TA/TB select how the tile is read:
+//   TA=0: A[m*lda + k]   TA=1: A[k*lda + m]      TB=0: B[k*ldb + n]   TB=1: B[n*ldb + k]
+// Epilogue: + bias[n], activation (0 none, 1 relu, 2 sigmoid).
+// ---------------------------------------------------------------------------------------
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
+                                              int64_t ldb, float* __restrict__ C, int64_t ldc, int M, int N, int K,
+                                              const float* __restrict__ bias, int act) {
+  constexpr int T = 64, KC = 16;
+  __shared__ float sa[KC][T + 4], sb[KC][T + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * T, n0 = blockIdx.x * T;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    for (int e = threadIdx.x; e < T * KC; e += 256) {
+      int r, k;
+      if (TA == 0) { r = e / KC; k = e % KC; } else { k = e / T; r = e % T; }   // keep the global read contiguous
+      float v = 0.f;
+      if (m0 + r < M && k0 + k < K) v = TA == 0 ? A[(int64_t)(m0 + r) * lda + k0 + k] : A[(int64_t)(k0 + k) * lda + m0 + r];
+      sa[k][r] = v;
+    }
+    for (int e = threadIdx.x; e < T * KC; e += 256) {
+      int c, k;
+      if (TB == 0) { k = e / T; c = e % T; } else { c = e / KC; k = e % KC; }
+      float v = 0.f;
+      if (n0 + c < N && k0 + k < K) v = TB == 0 ? Bm[(int64_t)(k0 + k) * ldb + n0 + c] : Bm[(int64_t)(n0 + c) * ldb + k0 + k];
+      sb[k][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sb[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (act == 1) v = fmaxf(v, 0.f);
+      else if (act == 2) v = orx_sigmoid(v);
+      C[(int64_t)m * ldc + n] = v;
+    }
+  }
+}
+
+template <int TA, int TB>
+static int launch_gemm(const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                       int K, const float* bias, int act, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  k_gemm<TA, TB><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, C, ldc, M, N, K, bias, act);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
+// y[B,out] = act(x[B,in] @ w[in,out] + bias)     (multi_layer_perceptron.py:9-16; Keras kernel is [in,out])
+extern "C" int orx_mlp_layer_fwd(orx_handle_t h, const float* x, int64_t ldx, int32_t B, int32_t in, const float* w,
+                                 const float* bias, int32_t out, int32_t act, float* y, int64_t ldy, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && x && w && y, "null pointer");
+  ORX_REQUIRE(B >= 0 && in > 0 && out > 0 && ldx >= in && ldy >= out && act >= 0 && act <= 2, "bad sizes");
+  if (B == 0) return ORX_OK;
+  ORX_CUDA(cudaSetDevice(h->device));
+  return launch_gemm<0, 0>(x, ldx, w, out, y, ldy, B, out, in, bias, act, (cudaStream_t)s);
+}
+
+// dz = dy * act'(y) in place; db[n] = sum_b dz[b,n]
+__global__ void k_act_bwd(const float* __restrict__ y, int64_t ldy, float* __restrict__ dy, int64_t lddy, int B,
+                          int N, int act) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * N) return;
+  const int b = (int)(i / N), n = (int)(i % N);
+  const float yv = y[(int64_t)b * ldy + n];
+  float g = dy[(int64_t)b * lddy + n];
+  if (act == 1) g = yv > 0.f ? g : 0.f;
+  else if (act == 2) g = g * yv * (1.f - yv);
+  dy[(int64_t)b * lddy + n] = g;
+}
+
+__global__ void __launch_bounds__(256) k_col_sum(const float* __restrict__ dz, int64_t ld, int B, int N,
+                                                 float* __restrict__ db) {
+  // block (32 cols x 8 row-lanes); deterministic: fixed row partition, smem tree
+  __shared__ float sh[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (n < N)
+    for (int b = r; b < B; b += 8) acc += dz[(int64_t)b * ld + n];
+  sh[r][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (r == 0 && n < N) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x & 31];
+    db[n] = t;
+  }
+}
+
+// Backward of one Dense layer.  dy (dL/dy, [B,out], ld lddy) is overwritten with dL/dz.
+// dw[in,out] = x^T dz ; db[out] = colsum(dz) ; dx[B,in] = dz w^T (skipped when dx == NULL).
+extern "C" int orx_mlp_layer_bwd(orx_handle_t h, const float* x, int64_t ldx, const float* y, int64_t ldy,
+                                 const float* w, int32_t B, int32_t in, int32_t out, int32_t act, float* dy,
+                                 int64_t lddy, float* dx, int64_t lddx, float* dw, float* db, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && x && y && w && dy && dw, "null pointer");
+  ORX_REQUIRE(B > 0 && in > 0 && out > 0 && act >= 0 && act <= 2, "bad sizes");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)s;
+  if (act != 0) {
+    const int64_t n = (int64_t)B * out;
+    k_act_bwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y, ldy, dy, lddy, B, out, act);
+    ORX_LAUNCH_CHECK();
+  }
+  if (db) {
+    k_col_sum<<<(out + 31) / 32, 256, 0, st>>>(dy, lddy, B, out, db);
+    ORX_LAUNCH_CHECK();
+  }
+  int rc = launch_gemm<1, 0>(x, ldx, dy, lddy, dw, out, in, out, B, nullptr, 0, st);   // dw = x^T dz
+  if (rc) return rc;
+  if (dx) rc = launch_gemm<0, 1>(dy, lddy, w, out, dx, lddx, B, in, out, nullptr, 0, st);   // dx = dz w^T
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// prediction loss (dlrm.py:52-55,72-73,97-98): optional clip to [thr, 1-thr], then Keras
+// MeanSquaredError (kind 0) or BinaryCrossentropy on probabilities (kind 1, eps = 1e-7 [TF-mem]).
+// pred_out = clipped prediction; dpred = dloss/d(raw pred); out4[0] = loss.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pred_loss(const float* __restrict__ pred, const float* __restrict__ label,
+                                                   int B, int kind, float thr, float* __restrict__ pred_out,
+                                                   float* __restrict__ dpred, float* partials) {
+  __shared__ float sh[256];
+  float acc = 0.f;
+  const float invB = 1.f / (float)B;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    float p = pred[b];
+    float pass = 1.f;
+    if (thr > 0.f && thr < 1.f) {
+      pass = (p >= thr && p <= 1.f - thr) ? 1.f : 0.f;
+      p = fminf(fmaxf(p, thr), 1.f - thr);
+    }
+    const float y = label[b];
+    float d;
+    if (kind == 0) {
+      acc += (y - p) * (y - p);
+      d = 2.f * (p - y) * invB;
+    } else {
+      const float eps = 1e-7f;
+      const float ph = fminf(fmaxf(p, eps), 1.f - eps);
+      acc += -(y * logf(ph + eps) + (1.f - y) * logf(1.f - ph + eps));
+      d = (p >= eps && p <= 1.f - eps) ? -(y / (ph + eps) - (1.f - y) / (1.f - ph + eps)) * invB : 0.f;
+    }
+    if (pred_out) pred_out[b] = p;
+    if (dpred) dpred[b] = d * pass;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = sh[0];
+    partials[2 * blockIdx.x + 1] = 0.f;
+  }
+}
+
+extern "C" int orx_pred_loss(orx_handle_t h, const float* pred, const float* label, int32_t B, int32_t kind,
+                             float clip_threshold, float* pred_out, float* dpred, float* out4, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && pred && label && out4, "null pointer");
+  ORX_REQUIRE(B > 0 && (kind == 0 || kind == 1), "bad sizes/kind");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)s;
+  int blocks = (B + 255) / 256;
+  if (blocks > 256) blocks = 256;
+  int rc = orx_ensure_partials(h, blocks, st);
+  if (rc) return rc;
+  k_pred_loss<<<blocks, 256, 0, st>>>(pred, label, B, kind, clip_threshold, pred_out, dpred, h->partials);
+  ORX_LAUNCH_CHECK();
+  return orx_launch_reduce_partials(h->partials, blocks, 1.0f / (float)B, out4, st);
+}

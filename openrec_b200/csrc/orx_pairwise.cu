@@ -38,6 +38,24 @@ __global__ void k_index_build(OrxHash hu, OrxHash hi, const int32_t* __restrict_
   }
 }
 
+__global__ void k_index_build_strided(OrxHash hu, const int32_t* __restrict__ a, int64_t stride, int64_t rows, int n,
+                                       int stage_all, int32_t* bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t id = a[(int64_t)i * stride];
+  if (id >= 0 && (int64_t)id < rows) orx_hash_insert(hu, id, stage_all);
+  else atomicAdd(bad, 1);
+}
+
+int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride, int64_t rows, int32_t n,
+                                   bool stage_all, cudaStream_t st) {
+  if (n <= 0) return ORX_OK;
+  k_index_build_strided<<<(n + 255) / 256, 256, 0, st>>>(c->hu, a, stride, rows, n, stage_all ? 1 : 0,
+                                                         c->counters + 3);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
 int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
                            const int32_t* b1, int64_t rows_b, int32_t nb, bool stage_all, cudaStream_t st) {
   const int total = na + (b1 ? 2 * nb : nb);
@@ -359,6 +377,237 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// cp.async variant: the rows of the next STAGES triplet groups are in flight in a per-warp shared-memory
+// ring (LDGSTS.128, no registers held while in flight), so memory-level parallelism is set by STAGES x
+// resident warps instead of by the register file.  Each lane copies and later reads only ITS OWN 16 bytes of
+// every row, so no cross-lane synchronisation is needed: cp.async.wait_group orders a thread's own copies.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void orx_cp_async16(float4* smem_dst, const float* gsrc, bool pred) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = pred ? 16 : 0;   // src-size 0 => the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void orx_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void orx_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int KIND, int OPT, int D, int CH, int MINB, int STAGES>
+__global__ void __launch_bounds__(256, MINB) k_pair_step_async(const PairArgs a) {
+  constexpr int G = (D / 4 < 32) ? D / 4 : 32;
+  constexpr int K = D / (4 * G);
+  constexpr int TPW = 32 / G;
+  constexpr int NG = CH / TPW;  // triplet groups per warp
+  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool STAGE_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
+  constexpr int NR = 3 + (S0 ? 3 : 0) + (S1 ? 3 : 0);  // rows per triplet in the ring
+  static_assert(CH % TPW == 0 && STAGES >= 1 && STAGES <= NG, "bad staging");
+  extern __shared__ float4 orx_ring[];
+
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int grp = lane / G, gl = lane % G;
+  const int t = warp * CH + lane;
+  float4* ring = orx_ring + (size_t)wib * STAGES * NR * K * 32 + lane;   // this lane's column of the warp's ring
+  auto slot = [&](int stage, int row, int k) -> float4* { return ring + ((stage * NR + row) * K + k) * 32; };
+
+  int u_id = 0, p_id = 0, n_id = 0, du = -1, dp = -1, dn = -1, flags = 0;
+  if (lane < CH && t < a.B) {
+    u_id = a.uid[t];
+    p_id = a.pid[t];
+    n_id = a.nid[t];
+    flags = (u_id >= 0 && u_id < a.rowsU && p_id >= 0 && p_id < a.rowsI && n_id >= 0 && n_id < a.rowsI) ? 1 : 0;
+  }
+
+  auto issue_var = [&](int g, int stage) {
+    const int src = g * TPW + grp;
+    const bool v = __shfl_sync(ORX_FULL, flags, src) & 1;
+    const int uu = __shfl_sync(ORX_FULL, u_id, src), pp = __shfl_sync(ORX_FULL, p_id, src),
+              nn = __shfl_sync(ORX_FULL, n_id, src);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int off = (k * G + gl) * 4;
+      orx_cp_async16(slot(stage, 0, k), v ? a.U + (int64_t)uu * D + off : a.U, v);
+      orx_cp_async16(slot(stage, 1, k), v ? a.I + (int64_t)pp * D + off : a.I, v);
+      orx_cp_async16(slot(stage, 2, k), v ? a.I + (int64_t)nn * D + off : a.I, v);
+    }
+  };
+  auto issue_slots = [&](int g, int stage) {
+    if (!S0) return;
+    const int src = g * TPW + grp;
+    const int fl = __shfl_sync(ORX_FULL, flags, src);
+    const int uu = __shfl_sync(ORX_FULL, u_id, src), pp = __shfl_sync(ORX_FULL, p_id, src),
+              nn = __shfl_sync(ORX_FULL, n_id, src);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int off = (k * G + gl) * 4;
+      orx_cp_async16(slot(stage, 3, k), (fl & 2) ? a.Us0 + (int64_t)uu * D + off : a.Us0, fl & 2);
+      orx_cp_async16(slot(stage, 4, k), (fl & 4) ? a.Is0 + (int64_t)pp * D + off : a.Is0, fl & 4);
+      orx_cp_async16(slot(stage, 5, k), (fl & 8) ? a.Is0 + (int64_t)nn * D + off : a.Is0, fl & 8);
+      if (S1) {
+        orx_cp_async16(slot(stage, 6, k), (fl & 2) ? a.Us1 + (int64_t)uu * D + off : a.Us1, fl & 2);
+        orx_cp_async16(slot(stage, 7, k), (fl & 4) ? a.Is1 + (int64_t)pp * D + off : a.Is1, fl & 4);
+        orx_cp_async16(slot(stage, 8, k), (fl & 8) ? a.Is1 + (int64_t)nn * D + off : a.Is1, fl & 8);
+      }
+    }
+  };
+
+  // variable rows of the first STAGES groups go out before the hash probes
+#pragma unroll
+  for (int g = 0; g < STAGES; ++g) issue_var(g, g);
+
+  float bp = 0.f, bn = 0.f, bps0 = 0.f, bps1 = 0.f, bns0 = 0.f, bns1 = 0.f;
+  if (flags & 1) {
+    const uint32_t cu = orx_hash_find(a.hu, u_id, &du);
+    const uint32_t cp = orx_hash_find(a.hi, p_id, &dp);
+    const uint32_t cn = orx_hash_find(a.hi, n_id, &dn);
+    bp = __ldcg(a.Bv + p_id);
+    bn = __ldcg(a.Bv + n_id);
+    if (!STAGE_ONLY) {
+      flags |= (cu == 1u ? 2 : 0) | (cp == 1u ? 4 : 0) | (cn == 1u ? 8 : 0);
+      if (S0) {
+        if (flags & 4) bps0 = __ldcg(a.Bs0 + p_id);
+        if (flags & 8) bns0 = __ldcg(a.Bs0 + n_id);
+      }
+      if (S1) {
+        if (flags & 4) bps1 = __ldcg(a.Bs1 + p_id);
+        if (flags & 8) bns1 = __ldcg(a.Bs1 + n_id);
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < STAGES; ++g) {
+    issue_slots(g, g);
+    orx_cp_commit();   // group g = slots(g) (+ every var row issued so far for g == 0)
+  }
+
+  float loss_acc = 0.f, l2_acc = 0.f, g_own = 0.f;
+#pragma unroll 1
+  for (int g = 0; g < NG; ++g) {
+    const int stage = g % STAGES;
+    orx_cp_wait<STAGES - 1>();
+    const int src = g * TPW + grp;
+    const int fl = __shfl_sync(ORX_FULL, flags, src);
+    const int uu = __shfl_sync(ORX_FULL, u_id, src), pp = __shfl_sync(ORX_FULL, p_id, src),
+              nn = __shfl_sync(ORX_FULL, n_id, src);
+    const int duj = __shfl_sync(ORX_FULL, du, src), dpj = __shfl_sync(ORX_FULL, dp, src),
+              dnj = __shfl_sync(ORX_FULL, dn, src);
+    const float bpj = __shfl_sync(ORX_FULL, bp, src), bnj = __shfl_sync(ORX_FULL, bn, src);
+    float4 u[K], p[K], n[K];
+    float s1 = 0.f, s2 = 0.f, sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      u[k] = *slot(stage, 0, k);
+      p[k] = *slot(stage, 1, k);
+      n[k] = *slot(stage, 2, k);
+      if (KIND == ORX_PAIR_BPR) {
+        s1 += dot4(u[k], p[k]);
+        s2 += dot4(u[k], n[k]);
+      } else {
+        s1 += sqd4(u[k], p[k]);
+        s2 += sqd4(u[k], n[k]);
+      }
+      sq += dot4(u[k], u[k]) + dot4(p[k], p[k]) + dot4(n[k], n[k]);
+    }
+    l2_acc += sq;
+    s1 = orx_group_sum<G>(s1);
+    s2 = orx_group_sum<G>(s2);
+    float lt, gsc;
+    pair_score<KIND>(s1, s2, bpj, bnj, a, &lt, &gsc);
+    const bool v = fl & 1;
+    if (!v) { lt = 0.f; gsc = 0.f; }
+    if (gl == 0) loss_acc += lt;
+    const float gbias = (KIND == ORX_PAIR_BPR) ? gsc : -gsc;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      const float val = __shfl_sync(ORX_FULL, gbias, q * G);
+      if (lane == g * TPW + q) g_own = val;
+    }
+    if (v) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int off = (k * G + gl) * 4;
+        float4 gu, gp, gn;
+        pair_row_grads<KIND>(gsc, a.c_l2, u[k], p[k], n[k], &gu, &gp, &gn);
+        float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0;
+        if (!STAGE_ONLY && (fl & 2)) {
+          const int64_t o = (int64_t)uu * D + off;
+          float4 a0 = S0 ? *slot(stage, 3, k) : z0, a1 = S1 ? *slot(stage, 6, k) : z1;
+          __stcg(reinterpret_cast<float4*>(a.U + o), orx_apply4<OPT>(u[k], gu, a0, a1, a.opt));
+          if (S0) __stcg(reinterpret_cast<float4*>(a.Us0 + o), a0);
+          if (S1) __stcg(reinterpret_cast<float4*>(a.Us1 + o), a1);
+        } else {
+          orx_red4(a.gu + (int64_t)duj * D + off, gu);
+        }
+        if (!STAGE_ONLY && (fl & 4)) {
+          const int64_t o = (int64_t)pp * D + off;
+          float4 a0 = S0 ? *slot(stage, 4, k) : z0, a1 = S1 ? *slot(stage, 7, k) : z1;
+          __stcg(reinterpret_cast<float4*>(a.I + o), orx_apply4<OPT>(p[k], gp, a0, a1, a.opt));
+          if (S0) __stcg(reinterpret_cast<float4*>(a.Is0 + o), a0);
+          if (S1) __stcg(reinterpret_cast<float4*>(a.Is1 + o), a1);
+        } else {
+          orx_red4(a.gi + (int64_t)dpj * D + off, gp);
+        }
+        if (!STAGE_ONLY && (fl & 8)) {
+          const int64_t o = (int64_t)nn * D + off;
+          float4 a0 = S0 ? *slot(stage, 5, k) : z0, a1 = S1 ? *slot(stage, 8, k) : z1;
+          __stcg(reinterpret_cast<float4*>(a.I + o), orx_apply4<OPT>(n[k], gn, a0, a1, a.opt));
+          if (S0) __stcg(reinterpret_cast<float4*>(a.Is0 + o), a0);
+          if (S1) __stcg(reinterpret_cast<float4*>(a.Is1 + o), a1);
+        } else {
+          orx_red4(a.gi + (int64_t)dnj * D + off, gn);
+        }
+      }
+    }
+    if (g + STAGES < NG) {   // refill the slot just consumed
+      issue_var(g + STAGES, stage);
+      issue_slots(g + STAGES, stage);
+    }
+    orx_cp_commit();         // one group per iteration (possibly empty) keeps wait_group<STAGES-1> exact
+  }
+
+  if (flags & 1) {
+    if (flags & 4) {
+      __stcg(a.Bv + p_id, orx_apply<OPT>(bp, g_own, bps0, bps1, a.opt));
+      if (S0) __stcg(a.Bs0 + p_id, bps0);
+      if (S1) __stcg(a.Bs1 + p_id, bps1);
+    } else {
+      atomicAdd(a.gb + dp, g_own);
+    }
+    if (flags & 8) {
+      __stcg(a.Bv + n_id, orx_apply<OPT>(bn, -g_own, bns0, bns1, a.opt));
+      if (S0) __stcg(a.Bs0 + n_id, bns0);
+      if (S1) __stcg(a.Bs1 + n_id, bns1);
+    } else {
+      atomicAdd(a.gb + dn, -g_own);
+    }
+    if (a.g_out) a.g_out[t] = (KIND == ORX_PAIR_BPR) ? g_own : -g_own;
+  } else if (a.g_out && lane < CH && t < a.B) {
+    a.g_out[t] = 0.f;
+  }
+
+  __shared__ float sred[8][2];
+  loss_acc = orx_group_sum<32>(loss_acc);
+  l2_acc = orx_group_sum<32>(l2_acc);
+  if (lane == 0) {
+    sred[wib][0] = loss_acc;
+    sred[wib][1] = l2_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, q = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      l += sred[w][0];
+      q += sred[w][1];
+    }
+    a.partials[2 * blockIdx.x] = l;
+    a.partials[2 * blockIdx.x + 1] = q;
+  }
+}
+
 // Any dim (e.g. the example's D=50): one triplet per warp-iteration, lanes stride the row.
 template <int KIND, int OPT>
 __global__ void __launch_bounds__(256) k_pair_step_generic(const PairArgs a) {
@@ -640,7 +889,7 @@ __global__ void __launch_bounds__(256) k_sparse_tail(const TailArgs a) {
 }
 
 int orx_launch_tail(orx_ctx* c, const TailArgs& ta, int opt_kind, cudaStream_t st) {
-  const int grid = c->num_sms * 2;
+  const int grid = c->num_sms * 8;  // ~1 staged row per warp: the tail is a latency chain, not bandwidth
   switch (opt_kind) {
     case ORX_OPT_SGD: k_sparse_tail<ORX_OPT_SGD><<<grid, 256, 0, st>>>(ta); break;
     case ORX_OPT_ADAGRAD: k_sparse_tail<ORX_OPT_ADAGRAD><<<grid, 256, 0, st>>>(ta); break;
@@ -668,6 +917,7 @@ int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t ro
 // Tuning variants of the D=128 kernel, selected with ORX_PAIR_VARIANT (A/B on the GPU):
 //   0 (default): 2 CTAs/SM, register double-buffer   1: 3 CTAs/SM, double-buffer
 //   2: 4 CTAs/SM, single buffer                      3: 3 CTAs/SM, single buffer
+//   4/5/6: cp.async shared-memory ring, (stages, CTAs/SM) = (4,2) / (3,3) / (2,4)
 static int pair_variant() {
   static int v = -1;
   if (v < 0) {
@@ -687,6 +937,15 @@ static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaS
     *n_partials = blocks;
     kern<<<blocks, 256, 0, st>>>(pa);
   };
+  auto go_async = [&](auto kern, int ch, int stages) {
+    constexpr int NRr = 3 + ((OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY) ? 3 : 0) + (LAZY ? 3 : 0);
+    const size_t smem = (size_t)8 * stages * NRr * (pa.D / 128 > 0 ? pa.D / 128 : 1) * 512;
+    const int nw = (B + ch - 1) / ch;
+    const int blocks = (nw + 7) / 8;
+    *n_partials = blocks;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<blocks, 256, smem, st>>>(pa);
+  };
   (void)n_warps_hint;
   switch (pa.D) {
     case 32: go(k_pair_step<KIND, OPT, 32, 8, 2, !LAZY>, 8); break;
@@ -696,6 +955,9 @@ static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaS
         case 1: go(k_pair_step<KIND, OPT, 128, 8, 3, !LAZY>, 8); break;
         case 2: go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8); break;
         case 3: go(k_pair_step<KIND, OPT, 128, 8, 3, false>, 8); break;
+        case 4: go_async(k_pair_step_async<KIND, OPT, 128, 8, 2, 4>, 8, 4); break;
+        case 5: go_async(k_pair_step_async<KIND, OPT, 128, 8, 3, 3>, 8, 3); break;
+        case 6: go_async(k_pair_step_async<KIND, OPT, 128, 8, 4, 2>, 8, 2); break;
         default: go(k_pair_step<KIND, OPT, 128, 8, 2, !LAZY>, 8); break;
       }
       break;

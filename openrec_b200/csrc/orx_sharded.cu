@@ -74,23 +74,23 @@ extern "C" int orx_owner_bucket(orx_handle_t h, const int32_t* ids, int32_t n, i
 // ---------------------------------------------------------------------------------------
 template <int OPT>
 __global__ void __launch_bounds__(256) k_sparse_apply(float* var, float* s0, float* s1, int64_t rows, int D,
-                                                      const int32_t* __restrict__ ids,
-                                                      const float* __restrict__ vals, int n, OrxHash hsh,
-                                                      float* gstage, OrxOptDev o) {
+                                                      const int32_t* __restrict__ ids, int64_t id_stride,
+                                                      const float* __restrict__ vals, int64_t val_ld, int n,
+                                                      OrxHash hsh, float* gstage, OrxOptDev o) {
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool STAGE_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= n) return;
-  const int32_t id = ids[b];
+  const int32_t id = ids[(int64_t)b * id_stride];
   if (id < 0 || (int64_t)id >= rows) return;
   int d = -1;
   uint32_t c = 0;
   if (lane == 0) c = orx_hash_find(hsh, id, &d);
   c = __shfl_sync(ORX_FULL, c, 0);
   d = __shfl_sync(ORX_FULL, d, 0);
-  const float* v = vals + (int64_t)b * D;
+  const float* v = vals + (int64_t)b * val_ld;
   if (!STAGE_ONLY && c == 1u) {
     float* w = var + (int64_t)id * D;
     for (int e = lane; e < D; e += 32) {
@@ -140,8 +140,24 @@ __global__ void __launch_bounds__(256) k_sparse_apply_tail(float* var, float* s0
   if (last && threadIdx.x < 4) counters[threadIdx.x] = 0;
 }
 
+static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
+                             const float* values, int64_t value_ld, int32_t n, const orx_opt_t* opt, orx_stream_t s);
+
 extern "C" int orx_sparse_apply(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
                                 int32_t n, const orx_opt_t* opt, orx_stream_t s) {
+  ORX_REQUIRE(tab != nullptr, "null table");
+  return sparse_apply_impl(h, tab, ids, 1, values, tab->dim, n, opt, s);
+}
+
+extern "C" int orx_sparse_apply_strided(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
+                                        const float* values, int64_t value_ld, int32_t n, const orx_opt_t* opt,
+                                        orx_stream_t s) {
+  ORX_REQUIRE(tab != nullptr && id_stride >= 1 && value_ld >= tab->dim, "bad strides");
+  return sparse_apply_impl(h, tab, ids, id_stride, values, value_ld, n, opt, s);
+}
+
+static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
+                             const float* values, int64_t value_ld, int32_t n, const orx_opt_t* opt, orx_stream_t s) {
   ORX_REQUIRE(h != nullptr && tab && tab->var && opt, "null pointer");
   ORX_REQUIRE(n >= 0 && tab->rows > 0 && tab->dim > 0, "bad sizes");
   ORX_REQUIRE(opt->kind >= ORX_OPT_SGD && opt->kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
@@ -158,13 +174,13 @@ extern "C" int orx_sparse_apply(orx_handle_t h, const orx_table_t* tab, const in
   const OrxOptDev o = orx_opt_to_dev(opt);
   // the user-side hash / staging pair serves as "the" table here
   if (n > 0) {
-    if ((rc = orx_launch_index_build(h, ids, tab->rows, n, nullptr, nullptr, 1, 0, dense, st))) return rc;
+    if ((rc = orx_launch_index_build_strided(h, ids, id_stride, tab->rows, n, dense, st))) return rc;
     const int blocks = (n + 7) / 8;
     switch (opt->kind) {
-      case ORX_OPT_SGD: k_sparse_apply<ORX_OPT_SGD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, values, n, h->hu, h->gu, o); break;
-      case ORX_OPT_ADAGRAD: k_sparse_apply<ORX_OPT_ADAGRAD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, values, n, h->hu, h->gu, o); break;
-      case ORX_OPT_ADAM_LAZY: k_sparse_apply<ORX_OPT_ADAM_LAZY><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, values, n, h->hu, h->gu, o); break;
-      default: k_sparse_apply<ORX_OPT_ADAM_DENSE><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, values, n, h->hu, h->gu, o); break;
+      case ORX_OPT_SGD: k_sparse_apply<ORX_OPT_SGD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, h->hu, h->gu, o); break;
+      case ORX_OPT_ADAGRAD: k_sparse_apply<ORX_OPT_ADAGRAD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, h->hu, h->gu, o); break;
+      case ORX_OPT_ADAM_LAZY: k_sparse_apply<ORX_OPT_ADAM_LAZY><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, h->hu, h->gu, o); break;
+      default: k_sparse_apply<ORX_OPT_ADAM_DENSE><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, h->hu, h->gu, o); break;
     }
     ORX_LAUNCH_CHECK();
   }

@@ -153,6 +153,56 @@ class Engine:
                                              self.stream()), "orx_owner_bucket")
         return counts, send_local, slot
 
+    def sparse_apply_strided(self, tab, ids2d, col, values3d, o):
+        """ids = ids2d[:, col] (int32 [n, F]); value rows = values3d[:, col, :] ([n, F, D]) -- no copies."""
+        n, F = ids2d.shape
+        D = values3d.shape[2]
+        _lib.check(self.lib.orx_sparse_apply_strided(
+            self.h, C.byref(tab), C.c_void_p(ids2d.data_ptr() + 4 * col), F,
+            C.c_void_p(values3d.data_ptr() + 4 * col * D), values3d.shape[1] * D, n, C.byref(o), self.stream()),
+            "orx_sparse_apply_strided")
+
+    # ---- DLRM pieces (2-D operands may be column-slices: the leading dimension is taken from stride(0)) ----
+    @staticmethod
+    def _ld(t):
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError("expected a 2-D float32 view with unit inner stride")
+        return t.stride(0)
+
+    def gather_strided(self, tab, ids2d, col, out2d):
+        n, F = ids2d.shape
+        _lib.check(self.lib.orx_gather_strided(self.h, _ptr(tab), tab.shape[0], tab.shape[1],
+                                               C.c_void_p(ids2d.data_ptr() + 4 * col), F, n, _ptr(out2d),
+                                               self._ld(out2d), None, self.stream()), "orx_gather_strided")
+
+    def mlp_fwd(self, x, w, bias, act, y):
+        _lib.check(self.lib.orx_mlp_layer_fwd(self.h, _ptr(x), self._ld(x), x.shape[0], w.shape[0], _ptr(w), _ptr(bias),
+                                              w.shape[1], act, _ptr(y), self._ld(y), self.stream()),
+                   "orx_mlp_layer_fwd")
+
+    def mlp_bwd(self, x, y, w, act, dy, dx, dw, db):
+        _lib.check(self.lib.orx_mlp_layer_bwd(self.h, _ptr(x), self._ld(x), _ptr(y), self._ld(y), _ptr(w), x.shape[0],
+                                              w.shape[0], w.shape[1], act, _ptr(dy), self._ld(dy), _ptr(dx),
+                                              self._ld(dx) if dx is not None else 0, _ptr(dw), _ptr(db),
+                                              self.stream()), "orx_mlp_layer_bwd")
+
+    def interact_fwd(self, emb3d, dense2d, self_interaction, mode, out2d):
+        B, Fm1, D = emb3d.shape
+        _lib.check(self.lib.orx_interact_fwd(self.h, _ptr(emb3d), Fm1 * D, _ptr(dense2d), self._ld(dense2d), B,
+                                             Fm1 + 1, D, int(self_interaction), mode, _ptr(out2d), self._ld(out2d),
+                                             self.stream()), "orx_interact_fwd")
+
+    def interact_bwd(self, emb3d, dense2d, dout2d, self_interaction, mode, demb3d, ddense2d):
+        B, Fm1, D = emb3d.shape
+        _lib.check(self.lib.orx_interact_bwd(self.h, _ptr(emb3d), Fm1 * D, _ptr(dense2d), self._ld(dense2d),
+                                             _ptr(dout2d), self._ld(dout2d), B, Fm1 + 1, D, int(self_interaction),
+                                             mode, _ptr(demb3d), Fm1 * D, _ptr(ddense2d), self._ld(ddense2d),
+                                             self.stream()), "orx_interact_bwd")
+
+    def pred_loss(self, pred, label, kind, clip, pred_out, dpred, out4):
+        _lib.check(self.lib.orx_pred_loss(self.h, _ptr(pred), _ptr(label), pred.numel(), kind, clip, _ptr(pred_out),
+                                          _ptr(dpred), _ptr(out4), self.stream()), "orx_pred_loss")
+
     # ---- pointwise ---------------------------------------------------------------------
     def pointwise_step(self, kind, user, item, bias, w, uid, iid, label, o, out4, a=1.0, b=1.0, use_sigmoid=False,
                        c_loss=1.0, c_l2=1.0):

@@ -1,10 +1,111 @@
-"""Dense / interaction operators behind keras Dense, MLP and SecondOrderFeatureInteraction (DLRM path).
-Filled in by the DLRM kernels; until then these fail loudly (no CPU / torch fallback)."""
+"""Dense / interaction operators behind keras Dense, MLP and SecondOrderFeatureInteraction, and the
+DLRM forward/backward composition -- all arithmetic in liborx (orx_mlp_layer_*, orx_interact_*,
+orx_gather_strided, orx_pred_loss); this module only sequences launches and owns activations."""
+from __future__ import annotations
+
+import torch
+
+from .. import native as N
+
+ACT = {None: 0, "linear": 0, "relu": 1, "sigmoid": 2}
 
 
 def dense_forward(x, kernel, bias, activation):
-    raise NotImplementedError("DLRM MLP kernels are not built yet")
+    x = x.reshape(-1, x.shape[-1]).contiguous()
+    y = torch.empty(x.shape[0], kernel.shape[1], dtype=torch.float32, device=x.device)
+    N.engine().mlp_fwd(x, kernel, bias, ACT[activation], y)
+    return y
+
+
+def interaction_width(F, self_interaction):
+    return F * (F + 1) // 2 if self_interaction else F * (F - 1) // 2
 
 
 def interaction_forward(feats, self_interaction, mode):
-    raise NotImplementedError("DLRM interaction kernel is not built yet")
+    """feats [B,F,D] (last feature = the dense vector) -> [B, F(F-+1)/2]."""
+    B, F, D = feats.shape
+    out = torch.empty(B, interaction_width(F, self_interaction), dtype=torch.float32, device=feats.device)
+    emb = feats[:, :F - 1, :].contiguous() if F > 1 else feats.new_empty(B, 0, D)
+    N.engine().interact_fwd(emb, feats[:, F - 1, :].contiguous(), self_interaction, 0 if mode == "reference" else 1,
+                            out)
+    return out
+
+
+class DLRMGraph:
+    """Forward / backward of DLRM.inference + loss (recommenders/dlrm.py:63-100) on preallocated views:
+    Z [B,T,D] embeddings, top_in [B, D+P] = (dense_vec | interactions) written in place by the last
+    bottom layer and the interaction kernel."""
+
+    def __init__(self, tables, bot, top, m_spa, self_interaction, mode, loss_kind, clip):
+        self.tables, self.bot, self.top = tables, bot, top          # lists of tensors / (w, b, act) triples
+        self.D, self.self_int, self.mode = m_spa, self_interaction, 0 if mode == "reference" else 1
+        self.loss_kind, self.clip = loss_kind, clip
+
+    def forward(self, dense, sparse, label=None, want_grad=False):
+        eng = N.engine()
+        dev = dense.device
+        B, T, D = dense.shape[0], len(self.tables), self.D
+        P = interaction_width(T + 1, self.self_int)
+        c = {"dense": dense, "sparse": sparse}
+        Z = c["Z"] = torch.empty(B, T, D, dtype=torch.float32, device=dev)
+        for k, tab in enumerate(self.tables):                        # dlrm.py:83-85
+            eng.gather_strided(tab, sparse, k, Z[:, k, :])
+        top_in = c["top_in"] = torch.empty(B, D + P, dtype=torch.float32, device=dev)
+        x, acts = dense, []
+        for l, (w, b, act) in enumerate(self.bot):                   # dlrm.py:87
+            last = l == len(self.bot) - 1
+            if last and w.shape[1] != D:
+                raise ValueError("the bottom MLP's last width must equal m_spa (tf.stack in the interaction)")
+            y = top_in[:, :D] if last else torch.empty(B, w.shape[1], dtype=torch.float32, device=dev)
+            eng.mlp_fwd(x, w, b, act, y)
+            acts.append(y)
+            x = y
+        c["bot_acts"] = acts
+        eng.interact_fwd(Z, top_in[:, :D], self.self_int, self.mode, top_in[:, D:])      # dlrm.py:89-92
+        x, acts = top_in, []
+        for w, b, act in self.top:
+            y = torch.empty(B, w.shape[1], dtype=torch.float32, device=dev)
+            eng.mlp_fwd(x, w, b, act, y)
+            acts.append(y)
+            x = y
+        c["top_acts"] = acts
+        raw = x.reshape(-1)
+        pred = c["pred"] = torch.empty(B, dtype=torch.float32, device=dev)
+        out4 = c["out4"] = torch.zeros(4, dtype=torch.float32, device=dev)
+        lab = label if label is not None else torch.zeros(B, dtype=torch.float32, device=dev)
+        c["dpred"] = torch.empty(B, dtype=torch.float32, device=dev) if want_grad else None
+        eng.pred_loss(raw, lab, self.loss_kind, self.clip, pred, c["dpred"], out4)       # dlrm.py:72-73,97-98
+        return c
+
+    def backward(self, c):
+        """-> (dZ [B,T,D], bottom [(dw, db)], top [(dw, db)])."""
+        eng = N.engine()
+        dense, top_in, Z = c["dense"], c["top_in"], c["Z"]
+        B, D = dense.shape[0], self.D
+        dev = dense.device
+        dy = c["dpred"].reshape(B, 1)
+        d_top_in = torch.empty_like(top_in)
+        top_g = [None] * len(self.top)
+        for l in range(len(self.top) - 1, -1, -1):
+            w, b, act = self.top[l]
+            x = top_in if l == 0 else c["top_acts"][l - 1]
+            dx = d_top_in if l == 0 else torch.empty(B, w.shape[0], dtype=torch.float32, device=dev)
+            dw = torch.empty_like(w)
+            db = torch.empty_like(b) if b is not None else None
+            eng.mlp_bwd(x, c["top_acts"][l], w, act, dy, dx, dw, db)
+            top_g[l] = (dw, db)
+            dy = dx
+        dZ = torch.empty_like(Z)
+        eng.interact_bwd(Z, top_in[:, :D], d_top_in[:, D:], self.self_int, self.mode, dZ, d_top_in[:, :D])
+        dy = d_top_in[:, :D]
+        bot_g = [None] * len(self.bot)
+        for l in range(len(self.bot) - 1, -1, -1):
+            w, b, act = self.bot[l]
+            x = dense if l == 0 else c["bot_acts"][l - 1]
+            dx = None if l == 0 else torch.empty(B, w.shape[0], dtype=torch.float32, device=dev)
+            dw = torch.empty_like(w)
+            db = torch.empty_like(b) if b is not None else None
+            eng.mlp_bwd(x, c["bot_acts"][l], w, act, dy, dx, dw, db)
+            bot_g[l] = (dw, db)
+            dy = dx
+        return dZ, bot_g, top_g

@@ -14,21 +14,30 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     out_path, kind, opt_kind = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    from fake_engine import FakeEngine
+    on_gpu = len(sys.argv) > 4 and sys.argv[4] == "gpu"
     from openrec_b200.sharded import ShardedPairwise
+    if on_gpu:   # the real kernels, one process per GPU over NCCL
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        from openrec_b200 import native
+        engine = native.engine(torch.device("cuda", rank))
+    else:        # host logic only: oracle-backed stand-in over gloo
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from fake_engine import FakeEngine
+        engine = FakeEngine()
+    dev = engine.device
     rng = np.random.default_rng(99)                       # same global problem on every rank
-    U, I, D, B = 61, 83, 16, 40
+    U, I, D, B = (61, 83, 16, 40) if not on_gpu else (1501, 2003, 128, 1024)
     sc = 0.05 if kind == 0 else 0.4
     user, item, bias = (rng.uniform(-sc, sc, s).astype(np.float32) for s in ((U, D), (I, D), (I, 1)))
-    m = ShardedPairwise(FakeEngine(), rank, world, U, I, D, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
+    m = ShardedPairwise(engine, rank, world, U, I, D, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
     m.load_global(user, item, bias)
     losses = []
     for step in range(3):
         ids = [rng.integers(0, n, B * world).astype(np.int32) for n in (U, I, I)]   # global batch
-        mine = [torch.from_numpy(a[rank * B:(rank + 1) * B].copy()) for a in ids]
-        losses.append(m.step(*mine).numpy().copy())
-    full = [t.numpy() for t in m.gather_global()]
+        mine = [torch.from_numpy(a[rank * B:(rank + 1) * B].copy()).to(dev) for a in ids]
+        losses.append(m.step(*mine).cpu().numpy().copy())
+    full = [t.cpu().numpy() for t in m.gather_global()]
     if rank == 0:
         np.savez(out_path, user=full[0], item=full[1], bias=full[2], losses=np.stack(losses))
     dist.destroy_process_group()

@@ -375,3 +375,72 @@ def test_full_size_bpr_adagrad(eng):
     mask = torch.ones(1000, dtype=torch.bool)
     mask[torch.from_numpy(rows_i[rows_i < 1000])] = False
     assert torch.equal(ti[:1000][mask.cuda()], untouched_before[mask.cuda()])   # untouched rows bit-identical
+
+
+# ---------------------------------------------------------------------------------------
+# un-fused sparse apply + sharded building blocks
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("optname", list(OPTS))
+@pytest.mark.parametrize("D,rows,n", [(1, 300, 500), (50, 400, 1000), (128, 3000, 4096)])
+def test_sparse_apply(eng, optname, D, rows, n):
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(seed_of("sparse", optname, D))
+    ok, lr = OPTS[optname]
+    var = rng.uniform(-0.3, 0.3, (rows, D))
+    st, dv = slots(ok, ("v", var))
+    tv = dev(var)
+    var = tv.cpu().numpy().astype(np.float64)
+    s = tuple(None if x is None else dev(x).cpu().numpy().astype(np.float64) for x in st["v"])
+    for step in (1, 2):
+        ids = rng.integers(0, rows, n).astype(np.int32)
+        vals = rng.standard_normal((n, D)).astype(np.float32)
+        eng.sparse_apply(N.table(tv, *dv["v"]), dev(ids, torch.int32), dev(vals), N.opt(ok, lr, step=step))
+        O.apply_sparse(ok, var, s[0], s[1], ids, vals.astype(np.float64), step, lr)
+        close(tv, var, atol=2e-5, what=f"var step {step}")
+        for j in (0, 1):
+            if s[j] is not None:
+                close(dv["v"][j], s[j], atol=2e-5, what=f"slot{j}")
+
+
+def test_owner_bucket(eng):
+    rng = np.random.default_rng(8)
+    for world in (2, 3, 8):
+        ids = rng.integers(0, 100000, 5000).astype(np.int32)
+        counts, send_local, slot = (t.cpu().numpy() for t in eng.owner_bucket(dev(ids, torch.int32), world))
+        assert np.array_equal(counts, np.bincount(ids % world, minlength=world))
+        assert sorted(slot.tolist()) == list(range(len(ids)))            # a permutation
+        assert np.array_equal(send_local[slot], ids // world)            # lookup i sits at slot[i]
+        owner_of_slot = np.repeat(np.arange(world), counts)
+        assert np.array_equal(owner_of_slot[slot], ids % world)          # buckets are contiguous per owner
+
+
+@pytest.mark.parametrize("kind", ["bpr", "ucml"])
+def test_pairwise_grad_slots(eng, kind):
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(9)
+    B, D, R = 300, 64, 4
+    sc = 0.05 if kind == "bpr" else 0.4
+    urows, irows, brows = rng.uniform(-sc, sc, (B, D)), rng.uniform(-sc, sc, (2 * B, D)), rng.uniform(-sc, sc, (2 * B, 1))
+    us, ps, ns = rng.permutation(B).astype(np.int32), rng.permutation(2 * B)[:B].astype(np.int32), None
+    rest = np.setdiff1d(np.arange(2 * B), ps)
+    ns = rng.permutation(rest).astype(np.int32)
+    tu, ti, tb = dev(urows), dev(irows), dev(brows)
+    u64, i64, b64 = (t.cpu().numpy().astype(np.float64) for t in (tu, ti, tb))
+    du, di, db = torch.zeros_like(tu), torch.zeros_like(ti), torch.zeros_like(tb)
+    out4 = torch.zeros(4, device="cuda")
+    k = N.ORX_PAIR_BPR if kind == "bpr" else N.ORX_PAIR_UCML
+    eng.pairwise_grad_slots(k, tu, ti, tb, dev(us, torch.int32), dev(ps, torch.int32), dev(ns, torch.int32),
+                            1.0 / (B * R), du, di, db, out4, 0.5, 1.0, 1.0)
+    if kind == "bpr":
+        loss, l2 = O.bpr_forward(u64, i64, b64, us, ps, ns)
+        gr = O.bpr_grads(u64, i64, b64, us, ps, ns, 1.0 / R, 1.0)
+        loss = loss / R
+    else:
+        loss, l2 = O.ucml_forward(u64, i64, b64, us, ps, ns, 0.5)
+        gr = O.ucml_grads(u64, i64, b64, us, ps, ns, 0.5)
+    close(out4[0], loss, rtol=2e-5), close(out4[1], l2, rtol=2e-5)
+    ref_u, ref_i, ref_b = np.zeros_like(u64), np.zeros_like(i64), np.zeros_like(b64)
+    ref_u[gr["user"][0]], ref_i[gr["item"][0]] = gr["user"][1], gr["item"][1]
+    ref_b[gr["bias"][0]] = gr["bias"][1].reshape(-1, 1)
+    tol = 1e-4 if kind == "ucml" else ATOL
+    close(du, ref_u, atol=tol), close(di, ref_i, atol=tol), close(db, ref_b, atol=tol)
