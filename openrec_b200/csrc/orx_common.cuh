@@ -31,7 +31,8 @@ void orx_set_error(const char* fmt, ...);
 #define ORX_LAUNCH_CHECK() ORX_CUDA(cudaGetLastError())
 
 // Open-addressing hash index over the ids of one table for one batch ("K9").
-// slot word: high 32 = occurrence count, low 32 = id+1 (0 = empty).
+// slot word: [63:33] epoch | [32] "seen more than once" | [31:0] id.  A slot whose epoch differs from the
+// current one is EMPTY, so the table is never cleared: every step just uses a new epoch (31 bits).
 struct OrxHash {
   unsigned long long* slots;  // [cap]
   int32_t* didx;              // [cap]  compact staging index of a staged row
@@ -39,6 +40,7 @@ struct OrxHash {
   int32_t* counter;           // number of staged rows
   uint32_t mask;
   int32_t shift;  // 32 - log2(cap)
+  uint32_t epoch;  // current epoch, >= 1
 };
 
 struct orx_ctx {
@@ -64,7 +66,14 @@ struct orx_ctx {
   int prof_on, prof_n, prof_cap;
   cudaEvent_t* prof_ev;  // [prof_cap*4]
   int32_t* bucket_cursor;  // owner-bucket scratch
+  uint32_t epoch;          // hash epoch of the last step
 };
+
+// start a new hash epoch (call once per step before the index build)
+static inline void orx_new_epoch(orx_ctx* c) {
+  c->epoch++;
+  c->hu.epoch = c->hi.epoch = c->epoch;
+}
 
 // record phase boundary k (0..3) of the current step on `st` when profiling is enabled
 static inline void orx_prof_mark(orx_ctx* c, int k, cudaStream_t st) {
@@ -92,48 +101,58 @@ struct OrxOptDev {
 
 __device__ __forceinline__ uint32_t orx_hash32(uint32_t id, int shift) { return (id * 2654435769u) >> shift; }
 
-// Insert one id.  mode 0: rows get a staging index on their SECOND occurrence (duplicates only);
+#define ORX_DUP_BIT (1ull << 32)
+__device__ __forceinline__ unsigned long long orx_slot_word(uint32_t epoch, int32_t id) {
+  return ((unsigned long long)epoch << 33) | (unsigned long long)(uint32_t)id;
+}
+
+// Insert one id.  mode 0: rows get a staging index when they are seen the SECOND time (duplicates only);
 // mode 1: on the FIRST occurrence (ADAM_DENSE stages every row); mode 2: never (pure dedup, censor).
-// Returns the pre-insert occurrence count.
+// Returns 0 if this call was the first occurrence of the id in this epoch, else 1.
 __device__ __forceinline__ uint32_t orx_hash_insert(const OrxHash& t, int32_t id, int mode) {
-  const uint32_t key = (uint32_t)id + 1u;
+  const unsigned long long mine = orx_slot_word(t.epoch, id);
   uint32_t h = orx_hash32((uint32_t)id, t.shift);
   while (true) {
-    // CAS first: the common case (empty slot) costs one L2 round trip instead of load + CAS
-    unsigned long long w = atomicCAS(t.slots + h, 0ull, (1ull << 32) | key);
-    if (w == 0ull) {
-      if (mode == 1) {
-        int d = atomicAdd(t.counter, 1);
-        t.didx[h] = d;
-        t.did[d] = id;
+    unsigned long long w = __ldcg(t.slots + h);
+    if ((uint32_t)(w >> 33) != t.epoch) {   // empty or stale: try to claim it
+      const unsigned long long old = atomicCAS(t.slots + h, w, mine);
+      if (old == w) {
+        if (mode == 1) {
+          const int d = atomicAdd(t.counter, 1);
+          t.didx[h] = d;
+          t.did[d] = id;
+        }
+        return 0u;
       }
-      return 0u;
+      w = old;                              // somebody else claimed it meanwhile (same epoch by construction)
     }
-    if ((uint32_t)w == key) {
-      unsigned long long old = atomicAdd(t.slots + h, 1ull << 32);
-      uint32_t c = (uint32_t)(old >> 32);
-      if (mode == 0 && c == 1u) {
-        int d = atomicAdd(t.counter, 1);
-        t.didx[h] = d;
-        t.did[d] = id;
+    if ((w & ~ORX_DUP_BIT) == mine) {
+      if (!(w & ORX_DUP_BIT)) {
+        const unsigned long long old = atomicOr(t.slots + h, ORX_DUP_BIT);
+        if (mode == 0 && !(old & ORX_DUP_BIT)) {   // this call made the row "shared": give it a staging slot
+          const int d = atomicAdd(t.counter, 1);
+          t.didx[h] = d;
+          t.did[d] = id;
+        }
       }
-      return c;
+      return 1u;
     }
     h = (h + 1) & t.mask;
   }
 }
 
-// Lookup an id known to be present.  Returns count; *d = staging index when count>1 || stage_all.
+// Lookup.  Returns 0 = absent, 1 = present once, 2 = present more than once; *d = staging index if the row
+// has one (duplicates in mode 0, every row in mode 1).
 __device__ __forceinline__ uint32_t orx_hash_find(const OrxHash& t, int32_t id, int32_t* d) {
-  const uint32_t key = (uint32_t)id + 1u;
+  const unsigned long long mine = orx_slot_word(t.epoch, id);
   uint32_t h = orx_hash32((uint32_t)id, t.shift);
   while (true) {
-    unsigned long long w = __ldg(t.slots + h);
-    if ((uint32_t)w == key) {
+    const unsigned long long w = __ldg(t.slots + h);
+    if ((w & ~ORX_DUP_BIT) == mine) {
       *d = __ldg(t.didx + h);
-      return (uint32_t)(w >> 32);
+      return (w & ORX_DUP_BIT) ? 2u : 1u;
     }
-    if ((uint32_t)w == 0u) {
+    if ((uint32_t)(w >> 33) != t.epoch) {
       *d = -1;
       return 0u;
     }

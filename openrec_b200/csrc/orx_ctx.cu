@@ -91,6 +91,7 @@ int orx_ensure_workspace(orx_ctx* c, int64_t B, int32_t dim, bool /*full_staging
   ORX_CUDA(cudaMemset(c->counters, 0, sizeof(int32_t) * 8));
   c->cap_B = nb;
   c->g_dim = nd;
+  c->epoch = 0;  // fresh (zeroed) tables: epochs restart at 1
   return ORX_OK;
 }
 

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "orx_common.cuh"
+#include "orx_pair.cuh"
 
 // ---------------------------------------------------------------------------------------
 // K9: batch index
@@ -50,6 +51,7 @@ __global__ void k_index_build_strided(OrxHash hu, const int32_t* __restrict__ a,
 int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride, int64_t rows, int32_t n,
                                    bool stage_all, cudaStream_t st) {
   if (n <= 0) return ORX_OK;
+  orx_new_epoch(c);
   k_index_build_strided<<<(n + 255) / 256, 256, 0, st>>>(c->hu, a, stride, rows, n, stage_all ? 1 : 0,
                                                          c->counters + 3);
   ORX_LAUNCH_CHECK();
@@ -60,6 +62,7 @@ int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t
                            const int32_t* b1, int64_t rows_b, int32_t nb, bool stage_all, cudaStream_t st) {
   const int total = na + (b1 ? 2 * nb : nb);
   if (total <= 0) return ORX_OK;
+  orx_new_epoch(c);
   k_index_build<<<(total + 255) / 256, 256, 0, st>>>(c->hu, c->hi, a, rows_a, na, b0, b1, rows_b, nb,
                                                     stage_all ? 1 : 0, c->counters + 3);
   ORX_LAUNCH_CHECK();
@@ -69,73 +72,6 @@ int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t
 // ---------------------------------------------------------------------------------------
 // K1/K2: fused step
 // ---------------------------------------------------------------------------------------
-struct PairArgs {
-  float *U, *Us0, *Us1;
-  float *I, *Is0, *Is1;
-  float *Bv, *Bs0, *Bs1;
-  int64_t rowsU, rowsI;
-  int D;
-  const int32_t *uid, *pid, *nid;
-  int B;
-  float margin, c_loss, c_l2, inv_B;
-  OrxOptDev opt;
-  OrxHash hu, hi;
-  float *gu, *gi, *gb;
-  float* partials;
-  float* g_out;
-};
-
-__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
-__device__ __forceinline__ float sqd4(float4 a, float4 b) {
-  float x = a.x - b.x, y = a.y - b.y, z = a.z - b.z, w = a.w - b.w;
-  return x * x + y * y + z * z + w * w;
-}
-// r = s*(a-b) + c*d
-__device__ __forceinline__ float4 axmb_pcd(float s, float4 a, float4 b, float c, float4 d) {
-  return make_float4(s * (a.x - b.x) + c * d.x, s * (a.y - b.y) + c * d.y, s * (a.z - b.z) + c * d.z,
-                     s * (a.w - b.w) + c * d.w);
-}
-// r = s*a + c*d
-__device__ __forceinline__ float4 sa_pcd(float s, float4 a, float c, float4 d) {
-  return make_float4(s * a.x + c * d.x, s * a.y + c * d.y, s * a.z + c * d.z, s * a.w + c * d.w);
-}
-
-// Per-sample score -> (loss term, gradient scalars).  BPR: x = (u.p+bp)-(u.n+bn),
-// loss term = -log sigmoid(max(x,-30)), g = -(c_loss/B) sigmoid(-y) [x>=-30]  (pairwise_log_loss.py:19-32).
-// UCML: h = margin - ((-|u-p|^2+bp) - (-|u-n|^2+bn)), loss term = max(h,0), a = c_loss [h>=0] (ucml.py:29-39).
-template <int KIND>
-__device__ __forceinline__ void pair_score(float s1, float s2, float bp, float bn, const PairArgs& a,
-                                           float* loss_term, float* g) {
-  if (KIND == ORX_PAIR_BPR) {
-    const float x = (s1 + bp) - (s2 + bn);
-    const float y = fmaxf(x, -30.f);
-    float ls, sn;
-    orx_logsig(y, &ls, &sn);
-    *loss_term = -ls;
-    *g = (x >= -30.f) ? -(a.c_loss * a.inv_B) * sn : 0.f;
-  } else {
-    const float h = a.margin - (((-s1) + bp) - ((-s2) + bn));
-    *loss_term = fmaxf(h, 0.f);
-    *g = (h >= 0.f) ? a.c_loss : 0.f;
-  }
-}
-
-// Row gradients from the scalar.
-template <int KIND>
-__device__ __forceinline__ void pair_row_grads(float g, float c2, float4 u, float4 p, float4 n, float4* gu,
-                                               float4* gp, float4* gn) {
-  if (KIND == ORX_PAIR_BPR) {
-    *gu = axmb_pcd(g, p, n, c2, u);
-    *gp = sa_pcd(g, u, c2, p);
-    *gn = sa_pcd(-g, u, c2, n);
-  } else {
-    const float t = 2.f * g;
-    *gu = axmb_pcd(t, n, p, c2, u);
-    *gp = axmb_pcd(t, p, u, c2, p);
-    *gn = axmb_pcd(t, u, n, c2, n);
-  }
-}
-
 template <int K, bool S0, bool S1>
 struct TripRegs {
   float4 u[K], p[K], n[K];
@@ -825,10 +761,7 @@ __global__ void __launch_bounds__(256) k_sparse_tail(const TailArgs a) {
       a.gb[d] = 0.f;
     }
   }
-  // clear both hash tables for the next step
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  for (uint32_t i = tid; i <= a.hu.mask; i += nth) a.hu.slots[i] = 0ull;
-  for (uint32_t i = tid; i <= a.hi.mask; i += nth) a.hi.slots[i] = 0ull;
+  // (the hash tables are not cleared: the next step uses a new epoch)
 
   __shared__ double sh[2][256];
   __shared__ bool last;
@@ -889,7 +822,7 @@ __global__ void __launch_bounds__(256) k_sparse_tail(const TailArgs a) {
 }
 
 int orx_launch_tail(orx_ctx* c, const TailArgs& ta, int opt_kind, cudaStream_t st) {
-  const int grid = c->num_sms * 8;  // ~1 staged row per warp: the tail is a latency chain, not bandwidth
+  const int grid = c->num_sms * 4;  // ~1-2 staged rows per warp: the tail is a latency chain, not bandwidth
   switch (opt_kind) {
     case ORX_OPT_SGD: k_sparse_tail<ORX_OPT_SGD><<<grid, 256, 0, st>>>(ta); break;
     case ORX_OPT_ADAGRAD: k_sparse_tail<ORX_OPT_ADAGRAD><<<grid, 256, 0, st>>>(ta); break;
@@ -915,14 +848,14 @@ int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t ro
 // host dispatch
 // ---------------------------------------------------------------------------------------
 // Tuning variants of the D=128 kernel, selected with ORX_PAIR_VARIANT (A/B on the GPU):
-//   0 (default): 2 CTAs/SM, register double-buffer   1: 3 CTAs/SM, double-buffer
-//   2: 4 CTAs/SM, single buffer                      3: 3 CTAs/SM, single buffer
+//   0: 2 CTAs/SM, register double-buffer             1: 3 CTAs/SM, double-buffer
+//   2 (default, fastest in profiles r1b/r1c): 4 CTAs/SM, single buffer   3: 3 CTAs/SM, single buffer
 //   4/5/6: cp.async shared-memory ring, (stages, CTAs/SM) = (4,2) / (3,3) / (2,4)
 static int pair_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ORX_PAIR_VARIANT");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 2;
   }
   return v;
 }
@@ -951,14 +884,14 @@ static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaS
     case 32: go(k_pair_step<KIND, OPT, 32, 8, 2, !LAZY>, 8); break;
     case 64: go(k_pair_step<KIND, OPT, 64, 8, 2, !LAZY>, 8); break;
     case 128:
-      switch (LAZY ? 0 : pair_variant()) {
+      switch (LAZY ? 3 : pair_variant()) {
+        case 0: go(k_pair_step<KIND, OPT, 128, 8, 2, !LAZY>, 8); break;
         case 1: go(k_pair_step<KIND, OPT, 128, 8, 3, !LAZY>, 8); break;
-        case 2: go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8); break;
         case 3: go(k_pair_step<KIND, OPT, 128, 8, 3, false>, 8); break;
         case 4: go_async(k_pair_step_async<KIND, OPT, 128, 8, 2, 4>, 8, 4); break;
         case 5: go_async(k_pair_step_async<KIND, OPT, 128, 8, 3, 3>, 8, 3); break;
         case 6: go_async(k_pair_step_async<KIND, OPT, 128, 8, 4, 2>, 8, 2); break;
-        default: go(k_pair_step<KIND, OPT, 128, 8, 2, !LAZY>, 8); break;
+        default: go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8); break;
       }
       break;
     case 256: go(k_pair_step<KIND, OPT, 256, 8, 2, !LAZY>, 8); break;

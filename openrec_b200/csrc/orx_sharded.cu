@@ -128,8 +128,6 @@ __global__ void __launch_bounds__(256) k_sparse_apply_tail(float* var, float* s0
       gstage[(int64_t)r * D + e] = 0.f;
     }
   }
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  for (uint32_t i = tid; i <= hsh.mask; i += nth) hsh.slots[i] = 0ull;
   __shared__ bool last;
   __syncthreads();
   if (threadIdx.x == 0) {

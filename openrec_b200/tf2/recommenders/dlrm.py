@@ -61,6 +61,7 @@ class DLRM(Model):
         """-> loss (a single lazy scalar, dlrm.py:63-74)."""
         node = StepNode(self, 1)
         node.inputs = self._inputs(dense_features, sparse_features, label)
+        self._graph(node.inputs[0].shape[1])   # keras builds the Dense layers during the first call
         return LazyScalar(node, {0: 1.0})
 
     def inference(self, dense_features, sparse_features):

@@ -136,3 +136,76 @@ def install():
     import openrec_b200.tf2.metrics.dict_mean as DM
     DM.device = core.device
     return fake
+
+
+# ---------------------------------------------------------------------------------------
+# DLRM pieces (oracle arithmetic on CPU views; in-place into the caller's tensors like liborx)
+# ---------------------------------------------------------------------------------------
+_ACT = {0: None, 1: "relu", 2: "sigmoid"}
+
+
+def _gather_strided(self, tab, ids2d, col, out2d):
+    out2d.copy_(tab[ids2d[:, col].long()])
+
+
+def _mlp_fwd(self, x, w, bias, act, y):
+    z = x.numpy().astype(np.float64) @ w.numpy().astype(np.float64)
+    if bias is not None:
+        z = z + bias.numpy()
+    y.copy_(torch.from_numpy(O._act(z, _ACT[act]).astype(np.float32)))
+
+
+def _mlp_bwd(self, x, y, w, act, dy, dx, dw, db):
+    dz = O._act_bwd(y.numpy().astype(np.float64), dy.numpy().astype(np.float64), _ACT[act])
+    dy.copy_(torch.from_numpy(dz.astype(np.float32)))
+    dw.copy_(torch.from_numpy((x.numpy().astype(np.float64).T @ dz).astype(np.float32)))
+    if db is not None:
+        db.copy_(torch.from_numpy(dz.sum(0).astype(np.float32)))
+    if dx is not None:
+        dx.copy_(torch.from_numpy((dz @ w.numpy().astype(np.float64).T).astype(np.float32)))
+
+
+def _feats(emb3d, dense2d):
+    return [emb3d[:, k, :].numpy().astype(np.float64) for k in range(emb3d.shape[1])] + [dense2d.numpy().astype(np.float64)]
+
+
+def _interact_fwd(self, emb3d, dense2d, self_interaction, mode, out2d):
+    r = O.second_order_interaction(_feats(emb3d, dense2d), bool(self_interaction), "reference" if mode == 0 else "dlrm")
+    out2d.copy_(torch.from_numpy(r.astype(np.float32)))
+
+
+def _interact_bwd(self, emb3d, dense2d, dout2d, self_interaction, mode, demb3d, ddense2d):
+    dZ = O.second_order_interaction_bwd(_feats(emb3d, dense2d), dout2d.numpy().astype(np.float64),
+                                        bool(self_interaction), "reference" if mode == 0 else "dlrm")
+    T = emb3d.shape[1]
+    demb3d.copy_(torch.from_numpy(dZ[:, :T, :].astype(np.float32)))
+    ddense2d.add_(torch.from_numpy(dZ[:, T, :].astype(np.float32)))
+
+
+def _pred_loss(self, pred, label, kind, clip, pred_out, dpred, out4):
+    p = pred.numpy().astype(np.float64)
+    passed = np.ones_like(p)
+    if 0.0 < clip < 1.0:
+        passed = ((p >= clip) & (p <= 1 - clip)).astype(np.float64)
+        p = np.clip(p, clip, 1 - clip)
+    loss, d = O.dlrm_loss(p, label.numpy(), "mse" if kind == 0 else "bce")
+    if pred_out is not None:
+        pred_out.copy_(torch.from_numpy(p.astype(np.float32)))
+    if dpred is not None:
+        dpred.copy_(torch.from_numpy((d * passed).astype(np.float32)))
+    out4[0] = float(loss)
+
+
+def _sparse_apply_strided(self, tab, ids2d, col, values3d, o):
+    O.apply_sparse(o.kind, _np(tab.var), _np(tab.s0), _np(tab.s1), ids2d[:, col].numpy(),
+                   values3d[:, col, :].numpy(), o.step, o.lr, o.eps, o.beta1, o.beta2)
+
+
+def _dense_apply(self, var, s0, s1, grad, o):
+    O.apply_dense(o.kind, var.numpy(), _np(s0), _np(s1), grad.numpy(), o.step, o.lr, o.eps, o.beta1, o.beta2)
+
+
+for _n, _f in (("gather_strided", _gather_strided), ("mlp_fwd", _mlp_fwd), ("mlp_bwd", _mlp_bwd),
+               ("interact_fwd", _interact_fwd), ("interact_bwd", _interact_bwd), ("pred_loss", _pred_loss),
+               ("sparse_apply_strided", _sparse_apply_strided), ("dense_apply", _dense_apply)):
+    setattr(FakeEngine, _n, _f)
