@@ -170,6 +170,19 @@ ORX_API int orx_sparse_apply_strided(orx_handle_t h, const orx_table_t* tab, con
 ORX_API int orx_owner_bucket(orx_handle_t h, const int32_t* ids, int32_t n, int32_t world, int32_t* counts,
                              int32_t* send_local, int32_t* slot, orx_stream_t s);
 
+/* Combined form used by openrec_b200/sharded.py: each rank stores ONE local table [user rows | item rows] of
+ * width ld = D+4 (item bias in column D), so a lookup is (owner, combined local row) whatever its table.
+ * orx_owner_bucket_combined: ids = uid | pid | nid (n_user user ids first); item lookups get the owner's user-row
+ *   count added to their local row.
+ * orx_pairwise_grad_rows: score/loss/gradients on the fetched rows (one row of width ld per lookup; slots index
+ *   the same buffer); gradients overwrite d_rows at the lookup's row (bias gradient in column D, padding zero). */
+ORX_API int orx_owner_bucket_combined(orx_handle_t h, const int32_t* ids, int32_t n, int32_t n_user, int64_t total_users,
+                                      int32_t world, int32_t* counts, int32_t* send_local, int32_t* slot, orx_stream_t s);
+ORX_API int orx_pairwise_grad_rows(orx_handle_t h, int32_t kind, const float* rows, int64_t ld, int32_t dim,
+                                   const int32_t* uslot, const int32_t* pslot, const int32_t* nslot, int32_t B,
+                                   float margin, float c_loss, float c_l2, float inv_B, float* d_rows, float* out4,
+                                   orx_stream_t s);
+
 /* ---- dense variables (GMF w, MLP kernels/biases): Keras dense apply ---------------------- */
 ORX_API int orx_dense_apply(orx_handle_t h, float* var, float* s0, float* s1, const float* grad, int64_t n,
                     const orx_opt_t* opt_host, orx_stream_t s);

@@ -60,6 +60,8 @@ SIGNATURES = {
     "orx_interact_bwd": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64,
                          _vp],
     "orx_pred_loss": [_vp, _vp, _vp, _i32, _i32, _f, _vp, _vp, _vp, _vp],
+    "orx_owner_bucket_combined": [_vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
+    "orx_pairwise_grad_rows": [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _f, _f, _f, _f, _vp, _vp, _vp],
     "orx_owner_bucket": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],
     "orx_pointwise_step": [_vp, _i32, _T, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _i32, _f, _f, _O, _vp, _vp],
     "orx_pointwise_fwd": [_vp, _i32, _T, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _i32, _vp, _vp],

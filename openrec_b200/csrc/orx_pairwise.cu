@@ -926,6 +926,17 @@ static int check_tables(const orx_table_t* user, const orx_table_t* item, const 
   return ORX_OK;
 }
 
+// ORX_FUSED=0 selects the three-launch path (index / step / tail); default: fused persistent kernel where an
+// instance exists (D = 128, SGD / Adagrad).
+static bool pair_fused_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ORX_FUSED");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, const orx_table_t* item,
                               const orx_table_t* bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
                               int B, float margin, float c_loss, float c_l2, const orx_opt_t* opt, float* out4,
@@ -939,10 +950,6 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
   const int D = user->dim;
   if ((rc = orx_ensure_workspace(c, B, D, opt->kind == ORX_OPT_ADAM_DENSE))) return rc;
   const bool dense = opt->kind == ORX_OPT_ADAM_DENSE;
-  orx_prof_mark(c, 0, st);
-  if ((rc = orx_launch_index_build(c, uid, user->rows, B, pid, nid, item->rows, B, dense, st))) return rc;
-  orx_prof_mark(c, 1, st);
-
   PairArgs pa;
   pa.U = user->var; pa.Us0 = user->s0; pa.Us1 = user->s1;
   pa.I = item->var; pa.Is0 = item->s0; pa.Is1 = item->s1;
@@ -951,10 +958,27 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
   pa.uid = uid; pa.pid = pid; pa.nid = nid; pa.B = B;
   pa.margin = margin; pa.c_loss = c_loss; pa.c_l2 = c_l2; pa.inv_B = 1.0f / (float)B;
   pa.opt = orx_opt_to_dev(opt);
-  pa.hu = c->hu; pa.hi = c->hi; pa.gu = c->gu; pa.gi = c->gi; pa.gb = c->gb;
-  pa.partials = c->partials; pa.g_out = nullptr;
-  if ((rc = orx_ensure_partials(c, (B + 63) / 64 + 8, st))) return rc;
+  pa.gu = c->gu; pa.gi = c->gi; pa.gb = c->gb;
+  pa.g_out = nullptr;
+  if ((rc = orx_ensure_partials(c, (B + 63) / 64 + 8 > c->num_sms ? (B + 63) / 64 + 8 : c->num_sms, st))) return rc;
   pa.partials = c->partials;
+  orx_prof_mark(c, 0, st);
+  if (pair_fused_enabled()) {   // one persistent cooperative launch (orx_pair_fused.cu)
+    orx_new_epoch(c);
+    pa.hu = c->hu; pa.hi = c->hi;
+    orx_prof_mark(c, 1, st);     // all phases live inside one kernel: it is reported as the "step" phase
+    rc = orx_launch_pair_fused(c, kind, opt->kind, pa, kind == ORX_PAIR_BPR ? pa.inv_B : 1.0f, out4, st);
+    if (rc == ORX_OK) {
+      orx_prof_mark(c, 2, st);
+      orx_prof_mark(c, 3, st);
+      orx_prof_next(c);
+      return ORX_OK;
+    }
+    if (rc != ORX_ERR_UNSUPPORTED) return rc;
+  }
+  if ((rc = orx_launch_index_build(c, uid, user->rows, B, pid, nid, item->rows, B, dense, st))) return rc;
+  orx_prof_mark(c, 1, st);
+  pa.hu = c->hu; pa.hi = c->hi;
   int n_partials = 0;
   rc = (kind == ORX_PAIR_BPR) ? launch_pair_step_kind<ORX_PAIR_BPR>(pa, opt->kind, st, &n_partials)
                               : launch_pair_step_kind<ORX_PAIR_UCML>(pa, opt->kind, st, &n_partials);
@@ -1026,6 +1050,7 @@ struct PairGradArgs {
   float *d_user, *d_pos, *d_neg, *d_bp, *d_bn, *g_out;
   float* partials;
   int slots;  // 1: outputs are indexed by the lookup's row (compact sharded form) instead of by triplet
+  int64_t ld;  // row stride of U / I / outputs in floats (0 => D); ld > D: item bias lives in column D of the row
 };
 
 template <int KIND>
@@ -1033,6 +1058,8 @@ __global__ void __launch_bounds__(256) k_pair_fwd_grad(const PairGradArgs a) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int D = a.D;
+  const int64_t ld = a.ld ? a.ld : D;
+  const bool bias_in_row = a.ld > D;
   float loss_acc = 0.f, l2_acc = 0.f;
   PairArgs sa;  // only the scalar fields pair_score reads
   sa.margin = a.margin;
@@ -1044,9 +1071,9 @@ __global__ void __launch_bounds__(256) k_pair_fwd_grad(const PairGradArgs a) {
     const int uu = a.uid[t], pp = a.pid[t], nn = a.nid[t];
     const bool ok = uu >= 0 && uu < a.rowsU && pp >= 0 && pp < a.rowsI && nn >= 0 && nn < a.rowsI;
     float s1 = 0.f, s2 = 0.f, sq = 0.f, bp = 0.f, bn = 0.f, lt = 0.f, g = 0.f;
-    const float* ur = a.U + (int64_t)uu * D;
-    const float* pr = a.I + (int64_t)pp * D;
-    const float* nr = a.I + (int64_t)nn * D;
+    const float* ur = a.U + (int64_t)uu * ld;
+    const float* pr = a.I + (int64_t)pp * ld;
+    const float* nr = a.I + (int64_t)nn * ld;
     if (ok) {
       for (int d = lane; d < D; d += 32) {
         const float u = ur[d], p = pr[d], n = nr[d];
@@ -1059,8 +1086,8 @@ __global__ void __launch_bounds__(256) k_pair_fwd_grad(const PairGradArgs a) {
         }
         sq += u * u + p * p + n * n;
       }
-      bp = a.Bv[pp];
-      bn = a.Bv[nn];
+      bp = bias_in_row ? pr[D] : a.Bv[pp];
+      bn = bias_in_row ? nr[D] : a.Bv[nn];
     }
     l2_acc += sq;
     s1 = orx_group_sum<32>(s1);
@@ -1085,9 +1112,9 @@ __global__ void __launch_bounds__(256) k_pair_fwd_grad(const PairGradArgs a) {
         }
         if (a.slots) {
           if (ok) {
-            a.d_user[(int64_t)uu * D + d] = gu;
-            a.d_pos[(int64_t)pp * D + d] = gp;
-            a.d_neg[(int64_t)nn * D + d] = gn;
+            a.d_user[(int64_t)uu * ld + d] = gu;
+            a.d_pos[(int64_t)pp * ld + d] = gp;
+            a.d_neg[(int64_t)nn * ld + d] = gn;
           }
         } else {
           const int64_t o = (int64_t)t * D + d;
@@ -1099,7 +1126,15 @@ __global__ void __launch_bounds__(256) k_pair_fwd_grad(const PairGradArgs a) {
     }
     if (lane == 0) {
       const float gbias = (KIND == ORX_PAIR_BPR) ? g : -g;
-      if (a.slots) {
+      if (a.slots && bias_in_row) {
+        if (ok) {   // column D = bias gradient (items) / 0 (users); remaining padding columns = 0
+          for (int64_t c = D; c < ld; ++c) {
+            a.d_user[(int64_t)uu * ld + c] = 0.f;
+            a.d_pos[(int64_t)pp * ld + c] = c == D ? gbias : 0.f;
+            a.d_neg[(int64_t)nn * ld + c] = c == D ? -gbias : 0.f;
+          }
+        }
+      } else if (a.slots) {
         if (ok) {
           a.d_bp[pp] = gbias;
           a.d_bn[nn] = -gbias;
@@ -1176,7 +1211,7 @@ static int pair_fwd_grad(orx_ctx* c, int kind, const orx_table_t* user, const or
   a.uid = uid; a.pid = pid; a.nid = nid; a.B = B;
   a.margin = margin; a.c_loss = c_loss; a.c_l2 = c_l2; a.inv_B = 1.0f / (float)B;
   a.d_user = d_user; a.d_pos = d_pos; a.d_neg = d_neg; a.d_bp = d_bp; a.d_bn = d_bn; a.g_out = g_out;
-  a.partials = c->partials; a.slots = 0;
+  a.partials = c->partials; a.slots = 0; a.ld = 0;
   if (kind == ORX_PAIR_BPR) k_pair_fwd_grad<ORX_PAIR_BPR><<<blocks, 256, 0, st>>>(a);
   else k_pair_fwd_grad<ORX_PAIR_UCML><<<blocks, 256, 0, st>>>(a);
   ORX_LAUNCH_CHECK();
@@ -1225,7 +1260,32 @@ extern "C" int orx_pairwise_grad_slots(orx_handle_t h, int32_t kind, const float
   a.uid = uslot; a.pid = pslot; a.nid = nslot; a.B = B;
   a.margin = margin; a.c_loss = c_loss; a.c_l2 = c_l2; a.inv_B = inv_B;
   a.d_user = d_user_rows; a.d_pos = d_item_rows; a.d_neg = d_item_rows; a.d_bp = d_bias_rows; a.d_bn = d_bias_rows;
-  a.g_out = nullptr; a.partials = h->partials; a.slots = 1;
+  a.g_out = nullptr; a.partials = h->partials; a.slots = 1; a.ld = 0;
+  if (kind == ORX_PAIR_BPR) k_pair_fwd_grad<ORX_PAIR_BPR><<<blocks, 256, 0, st>>>(a);
+  else k_pair_fwd_grad<ORX_PAIR_UCML><<<blocks, 256, 0, st>>>(a);
+  ORX_LAUNCH_CHECK();
+  return orx_launch_reduce_partials(h->partials, blocks * 8, kind == ORX_PAIR_BPR ? inv_B : 1.f, out4, st);
+}
+
+extern "C" int orx_pairwise_grad_rows(orx_handle_t h, int32_t kind, const float* rows, int64_t ld, int32_t dim,
+                                      const int32_t* uslot, const int32_t* pslot, const int32_t* nslot, int32_t B,
+                                      float margin, float c_loss, float c_l2, float inv_B, float* d_rows, float* out4,
+                                      orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && rows && uslot && pslot && nslot && d_rows && out4, "null pointer");
+  ORX_REQUIRE(kind == ORX_PAIR_BPR || kind == ORX_PAIR_UCML, "unknown pairwise kind");
+  ORX_REQUIRE(B > 0 && dim > 0 && ld > dim, "bad sizes (ld must exceed dim: the bias lives in column dim)");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)s;
+  const int nw = (B + 7) / 8, blocks = (nw + 7) / 8;
+  int rc = orx_ensure_partials(h, blocks * 8, st);
+  if (rc) return rc;
+  PairGradArgs a;
+  a.U = rows; a.I = rows; a.Bv = nullptr;
+  a.rowsU = 3 * (int64_t)B; a.rowsI = 3 * (int64_t)B; a.D = dim;
+  a.uid = uslot; a.pid = pslot; a.nid = nslot; a.B = B;
+  a.margin = margin; a.c_loss = c_loss; a.c_l2 = c_l2; a.inv_B = inv_B;
+  a.d_user = d_rows; a.d_pos = d_rows; a.d_neg = d_rows; a.d_bp = nullptr; a.d_bn = nullptr;
+  a.g_out = nullptr; a.partials = h->partials; a.slots = 1; a.ld = ld;
   if (kind == ORX_PAIR_BPR) k_pair_fwd_grad<ORX_PAIR_BPR><<<blocks, 256, 0, st>>>(a);
   else k_pair_fwd_grad<ORX_PAIR_UCML><<<blocks, 256, 0, st>>>(a);
   ORX_LAUNCH_CHECK();

@@ -45,6 +45,42 @@ __global__ void k_owner_scatter(const int32_t* __restrict__ ids, int n, int R, i
   slot[i] = s;
 }
 
+// combined form: lookups i >= n_user are item lookups; their local row is offset by the owner's user-row count
+__global__ void k_owner_scatter_combined(const int32_t* __restrict__ ids, int n, int n_user, int64_t U, int R,
+                                         int32_t* cursor, int32_t* __restrict__ send_local,
+                                         int32_t* __restrict__ slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t id = ids[i];
+  const int r = id >= 0 ? id % R : 0;
+  const int s = atomicAdd(cursor + r, 1);
+  const int32_t user_rows_on_r = (int32_t)((U - r + R - 1) / R);
+  send_local[s] = id >= 0 ? id / R + (i >= n_user ? user_rows_on_r : 0) : -1;
+  slot[i] = s;
+}
+
+extern "C" int orx_owner_bucket_combined(orx_handle_t h, const int32_t* ids, int32_t n, int32_t n_user,
+                                         int64_t total_users, int32_t world, int32_t* counts, int32_t* send_local,
+                                         int32_t* slot, orx_stream_t s) {
+  ORX_REQUIRE(h != nullptr && ids && counts && send_local && slot, "null pointer");
+  ORX_REQUIRE(n >= 0 && n_user >= 0 && n_user <= n && world >= 1 && world <= 1024 && total_users > 0, "bad sizes");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)s;
+  ORX_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * world, st));
+  if (n == 0) return ORX_OK;
+  if (!h->bucket_cursor) ORX_CUDA(cudaMalloc(&h->bucket_cursor, sizeof(int32_t) * 1024));
+  int blocks = (n + 255) / 256;
+  if (blocks > h->num_sms * 4) blocks = h->num_sms * 4;
+  k_owner_hist<<<blocks, 256, sizeof(int32_t) * world, st>>>(ids, n, world, counts);
+  ORX_LAUNCH_CHECK();
+  k_owner_scan<<<1, 32, 0, st>>>(counts, world, h->bucket_cursor);
+  ORX_LAUNCH_CHECK();
+  k_owner_scatter_combined<<<(n + 255) / 256, 256, 0, st>>>(ids, n, n_user, total_users, world, h->bucket_cursor,
+                                                            send_local, slot);
+  ORX_LAUNCH_CHECK();
+  return ORX_OK;
+}
+
 extern "C" int orx_owner_bucket(orx_handle_t h, const int32_t* ids, int32_t n, int32_t world, int32_t* counts,
                                 int32_t* send_local, int32_t* slot, orx_stream_t s) {
   ORX_REQUIRE(h != nullptr && ids && counts && send_local && slot, "null pointer");
@@ -53,11 +89,8 @@ extern "C" int orx_owner_bucket(orx_handle_t h, const int32_t* ids, int32_t n, i
   cudaStream_t st = (cudaStream_t)s;
   ORX_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * world, st));
   if (n == 0) return ORX_OK;
-  int32_t* cursor = h->counters + 4;  // needs `world` ints: reuse a dedicated scratch
-  if (world > 4) {
-    if (!h->bucket_cursor) ORX_CUDA(cudaMalloc(&h->bucket_cursor, sizeof(int32_t) * 1024));
-    cursor = h->bucket_cursor;
-  }
+  if (!h->bucket_cursor) ORX_CUDA(cudaMalloc(&h->bucket_cursor, sizeof(int32_t) * 1024));
+  int32_t* cursor = h->bucket_cursor;
   int blocks = (n + 255) / 256;
   if (blocks > h->num_sms * 4) blocks = h->num_sms * 4;
   k_owner_hist<<<blocks, 256, sizeof(int32_t) * world, st>>>(ids, n, world, counts);

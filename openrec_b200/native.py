@@ -203,6 +203,24 @@ class Engine:
         _lib.check(self.lib.orx_pred_loss(self.h, _ptr(pred), _ptr(label), pred.numel(), kind, clip, _ptr(pred_out),
                                           _ptr(dpred), _ptr(out4), self.stream()), "orx_pred_loss")
 
+    def owner_bucket_combined(self, ids, n_user, total_users, world):
+        """ids = uid | pid | nid -> (counts[world], send_local[n] combined local rows, slot[n])."""
+        n = ids.numel()
+        counts = torch.empty(world, dtype=torch.int32, device=ids.device)
+        send_local = torch.empty(n, dtype=torch.int32, device=ids.device)
+        slot = torch.empty(n, dtype=torch.int32, device=ids.device)
+        _lib.check(self.lib.orx_owner_bucket_combined(self.h, _ptr(ids), n, n_user, total_users, world, _ptr(counts),
+                                                      _ptr(send_local), _ptr(slot), self.stream()),
+                   "orx_owner_bucket_combined")
+        return counts, send_local, slot
+
+    def pairwise_grad_rows(self, kind, rows, dim, uslot, pslot, nslot, inv_B, d_rows, out4, margin=0.5, c_loss=1.0,
+                           c_l2=1.0):
+        _lib.check(self.lib.orx_pairwise_grad_rows(self.h, kind, _ptr(rows), rows.shape[1], dim, _ptr(uslot),
+                                                   _ptr(pslot), _ptr(nslot), uslot.numel(), margin, c_loss, c_l2,
+                                                   inv_B, _ptr(d_rows), _ptr(out4), self.stream()),
+                   "orx_pairwise_grad_rows")
+
     # ---- pointwise ---------------------------------------------------------------------
     def pointwise_step(self, kind, user, item, bias, w, uid, iid, label, o, out4, a=1.0, b=1.0, use_sigmoid=False,
                        c_loss=1.0, c_l2=1.0):

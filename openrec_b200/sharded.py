@@ -4,16 +4,16 @@ The reference is single-device; this is the scale-out of the same synchronous st
 row r of every table lives on rank ``r % R`` at local row ``r // R`` (optimizer slots alongside);
 each rank owns B triplets of the global batch.  One step =
 
-  1. orx_owner_bucket      : sort this rank's 3B lookups by owner                      (liborx)
-  2. all-to-all            : lookup counts, then local-row ids, to the owners          (NCCL over NVLink)
+  1. orx_owner_bucket_combined: sort this rank's 3B lookups by owner                   (liborx)
+  2. all-to-all            : lookup counts, then combined local-row ids, to the owners (NCCL over NVLink)
   3. orx_gather            : owners read the requested rows from their shard          (liborx)
   4. all-to-all            : rows back to the requesters
-  5. orx_pairwise_grad_slots: score, loss and per-lookup gradient rows, in place of the
-                             rows' slots (pre-step values everywhere: nothing has been written yet)
+  5. orx_pairwise_grad_rows: score, loss and per-lookup gradient rows
+                             (pre-step values everywhere: nothing has been written yet)
   6. all-to-all            : gradient rows to the owners
   7. orx_sparse_apply      : owners sum duplicates (across ALL ranks' lookups) and apply the
                              optimizer once per unique row                             (liborx)
-  8. all-reduce            : (loss, l2_loss)
+  8. all-reduce            : (loss, l2_loss), only when the caller asks for the global value
 
 ``torch.distributed`` is plumbing (one process per GPU, NCCL; gloo in the CPU logic tests); every
 arithmetic op is a liborx kernel reached through ``eng``.
@@ -36,98 +36,87 @@ def _a2a(out, inp, out_splits, in_splits):
 
 class ShardedPairwise:
     """BPR (kind 0) / UCML (kind 1) with row-sharded tables.  ``eng`` is a native.Engine (or the
-    oracle-backed stand-in of tests/fake_engine.py on CPU)."""
+    oracle-backed stand-in of tests/fake_engine.py on CPU).
+
+    Local storage is ONE combined table ``[user rows | item rows, D+4]`` per rank (item bias in column D, three
+    padding columns keep rows 16-byte aligned), with optimizer slots of the same shape: a lookup is then just
+    (owner, combined local row), and a step needs four collectives -- counts, ids, rows, gradient rows."""
+
+    PAD = 4
 
     def __init__(self, eng, rank, world, total_users, total_items, dim, *, kind=0, opt_kind=1, lr=0.05, eps=1e-7,
                  beta1=0.9, beta2=0.999, margin=0.5, seed=0, init=True):
         self.eng, self.rank, self.world = eng, rank, world
         self.U, self.I, self.D = total_users, total_items, dim
+        self.W = dim + self.PAD
         self.kind, self.opt_kind, self.lr, self.eps, self.b1, self.b2, self.margin = kind, opt_kind, lr, eps, beta1, beta2, margin
         self.iterations = 0
         dev = eng.device
-        ru = (total_users - rank + world - 1) // world     # rows r with r % world == rank
-        ri = (total_items - rank + world - 1) // world
-        self.user = torch.empty(ru, dim, dtype=torch.float32, device=dev)
-        self.item = torch.empty(ri, dim, dtype=torch.float32, device=dev)
-        self.bias = torch.empty(ri, 1, dtype=torch.float32, device=dev)
+        self.ru = (total_users - rank + world - 1) // world     # rows r with r % world == rank
+        self.ri = (total_items - rank + world - 1) // world
+        self.table = torch.zeros(self.ru + self.ri, self.W, dtype=torch.float32, device=dev)
         if init:
-            for k, t in enumerate((self.user, self.item, self.bias)):
-                eng.fill_uniform(t, -0.05, 0.05, seed * 1000003 + rank * 17 + k)
+            tmp = torch.empty(self.ru + self.ri, dim + 1, dtype=torch.float32, device=dev)
+            eng.fill_uniform(tmp, -0.05, 0.05, seed * 1000003 + rank * 17)
+            self.table[:, :dim + 1] = tmp
+            self.table[:self.ru, dim] = 0.0                      # users have no bias column
+            del tmp
         n_slots = {0: 0, 1: 1, 2: 2, 3: 2}[opt_kind]
         fill = 0.1 if opt_kind == 1 else 0.0
-        self.slots = [[torch.full_like(t, fill) for _ in range(n_slots)] + [None] * (2 - n_slots)
-                      for t in (self.user, self.item, self.bias)]
-        self.launches_per_step = 3 * 3 + 3 + 2 + 3 * 2   # buckets, gathers, grad+reduce, sparse applies (+tails)
+        self.slots = [torch.full_like(self.table, fill) for _ in range(n_slots)] + [None] * (2 - n_slots)
+        self.launches_per_step = 3 + 1 + 2 + 3   # bucket(3) gather(1) grad+reduce(2) sparse_apply(3)
+        self._loss_local = None
 
-    def _tables(self):
-        return [self.eng.make_table(t, *s) for t, s in zip((self.user, self.item, self.bias), self.slots)]
-
-    def step(self, uid, pid, nid, c_loss=1.0, c_l2=1.0):
-        """uid/pid/nid: this rank's int32 GLOBAL ids on the device.  Returns a [2] tensor
-        (global loss, global l2_loss) on the device."""
-        eng, R, D = self.eng, self.world, self.D
+    def step(self, uid, pid, nid, c_loss=1.0, c_l2=1.0, reduce_loss=True):
+        """uid/pid/nid: this rank's int32 GLOBAL ids on the device.  Returns a [2] device tensor: the global
+        (loss, l2_loss) when ``reduce_loss`` (one extra all-reduce), else this rank's partial sums."""
+        eng, R, D, W = self.eng, self.world, self.D, self.W
         B = uid.numel()
         dev = uid.device
         self.iterations += 1
-        items = torch.cat([pid, nid])
-        cu, send_u, slot_u = eng.owner_bucket(uid, R)
-        ci, send_i, slot_i = eng.owner_bucket(items, R)
-        counts = torch.stack([cu, ci], 1).contiguous()
+        ids = torch.cat([uid, pid, nid])
+        counts, send_local, slot = eng.owner_bucket_combined(ids, B, self.U, R)
         rcounts = torch.empty_like(counts)
         dist.all_to_all_single(rcounts, counts)
-        host = torch.cat([counts, rcounts]).cpu()                       # the step's one host sync
-        su, si = host[:R, 0].tolist(), host[:R, 1].tolist()
-        ru, ri = host[R:, 0].tolist(), host[R:, 1].tolist()
-        req_u = torch.empty(sum(ru), dtype=torch.int32, device=dev)
-        req_i = torch.empty(sum(ri), dtype=torch.int32, device=dev)
-        _a2a(req_u, send_u, ru, su)
-        _a2a(req_i, send_i, ri, si)
-        # owners: fetch rows of their shard, send them back
-        rows_u, rows_i, rows_b = eng.gather(self.user, req_u), eng.gather(self.item, req_i), eng.gather(self.bias, req_i)
-        got_u = torch.empty(B, D, dtype=torch.float32, device=dev)
-        got_i = torch.empty(2 * B, D, dtype=torch.float32, device=dev)
-        got_b = torch.empty(2 * B, 1, dtype=torch.float32, device=dev)
-        _a2a(got_u, rows_u, su, ru)
-        _a2a(got_i, rows_i, si, ri)
-        _a2a(got_b, rows_b, si, ri)
-        # requesters: gradients of this rank's triplets, written over the rows' slots
+        host = torch.stack([counts, rcounts]).cpu()                    # the step's one host sync
+        sc, rc = host[0].tolist(), host[1].tolist()
+        req = torch.empty(sum(rc), dtype=torch.int32, device=dev)
+        _a2a(req, send_local, rc, sc)
+        rows = eng.gather(self.table, req)                             # owners read their shard
+        got = torch.empty(3 * B, W, dtype=torch.float32, device=dev)
+        _a2a(got, rows, sc, rc)
         out4 = torch.zeros(4, dtype=torch.float32, device=dev)
-        d_u, d_i, d_b = torch.empty_like(got_u), torch.empty_like(got_i), torch.empty_like(got_b)
-        eng.pairwise_grad_slots(self.kind, got_u, got_i, got_b, slot_u, slot_i[:B].contiguous(),
-                                slot_i[B:].contiguous(), 1.0 / (B * R), d_u, d_i, d_b, out4, self.margin, c_loss, c_l2)
-        # gradients to the owners
-        g_u, g_i, g_b = torch.empty_like(rows_u), torch.empty_like(rows_i), torch.empty_like(rows_b)
-        _a2a(g_u, d_u, ru, su)
-        _a2a(g_i, d_i, ri, si)
-        _a2a(g_b, d_b, ri, si)
-        # owners: dedup across every rank's lookups, optimizer once per unique row
+        d_got = torch.empty_like(got)
+        eng.pairwise_grad_rows(self.kind, got, D, slot[:B], slot[B:2 * B], slot[2 * B:], 1.0 / (B * R), d_got, out4,
+                               self.margin, c_loss, c_l2)
+        g_rows = torch.empty_like(rows)
+        _a2a(g_rows, d_got, rc, sc)
         o = eng.make_opt(self.opt_kind, self.lr, self.eps, self.b1, self.b2, self.iterations)
-        tu, ti, tb = self._tables()
-        eng.sparse_apply(tu, req_u, g_u, o)
-        eng.sparse_apply(ti, req_i, g_i, o)
-        eng.sparse_apply(tb, req_i, g_b, o)
+        eng.sparse_apply(eng.make_table(self.table, *self.slots), req, g_rows, o)   # dedup across ALL ranks' lookups
         out = out4[:2].clone()
-        dist.all_reduce(out)
+        if reduce_loss:
+            dist.all_reduce(out)
         return out
 
     # ---- helpers for tests: assemble / scatter the global tables
     def load_global(self, user, item, bias):
-        r, R = self.rank, self.world
-        self.user.copy_(torch.as_tensor(user[r::R], dtype=torch.float32))
-        self.item.copy_(torch.as_tensor(item[r::R], dtype=torch.float32))
-        self.bias.copy_(torch.as_tensor(bias[r::R], dtype=torch.float32))
+        r, R, D = self.rank, self.world, self.D
+        self.table[:self.ru, :D] = torch.as_tensor(user[r::R], dtype=torch.float32)
+        self.table[self.ru:, :D] = torch.as_tensor(item[r::R], dtype=torch.float32)
+        self.table[self.ru:, D] = torch.as_tensor(bias[r::R], dtype=torch.float32).reshape(-1)
 
     def gather_global(self):
         """-> (user, item, bias) full tables on every rank (test helper; sizes must be small)."""
+        D = self.D
         outs = []
-        for t, total in ((self.user, self.U), (self.item, self.I), (self.bias, self.I)):
+        for t, total in ((self.table[:self.ru, :D], self.U), (self.table[self.ru:, :D], self.I),
+                         (self.table[self.ru:, D:D + 1], self.I)):
             per = (total + self.world - 1) // self.world
             pad = torch.zeros(per, t.shape[1], dtype=t.dtype, device=t.device)
             pad[:t.shape[0]] = t
             parts = [torch.empty_like(pad) for _ in range(self.world)]
             dist.all_gather(parts, pad)
-            full = torch.stack(parts, 1).reshape(per * self.world, t.shape[1])[:total]   # row = local*R + rank
-            outs.append(full)
+            outs.append(torch.stack(parts, 1).reshape(per * self.world, t.shape[1])[:total])   # row = local*R + rank
         return outs
 
 
@@ -147,13 +136,13 @@ def bench(args, rank, world, eng, barrier):
     dev_ids = [tuple(x.to(dev) for x in b) for b in host_ids]
     clocks = B.ClockSampler(dev.index or 0) if rank == 0 else None
     for i in range(W):
-        model.step(*dev_ids[i % B.N_BATCHES])
+        model.step(*dev_ids[i % B.N_BATCHES], reduce_loss=False)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
     for i in range(K):
-        model.step(*dev_ids[i % B.N_BATCHES])
+        model.step(*dev_ids[i % B.N_BATCHES], reduce_loss=False)   # loss stays a per-rank partial on the device
     e1.record()
     barrier()
     t1 = time.time()
@@ -167,9 +156,19 @@ def bench(args, rank, world, eng, barrier):
     barrier()
     t0 = time.time()
     e0.record()
+    pinned = [torch.zeros(2).pin_memory() for _ in range(2)]
+    prev = None
     for i in range(K):
-        out = model.step(*(x.to(dev, non_blocking=True) for x in host_ids[i % B.N_BATCHES]))
-        last = out.cpu()
+        out = model.step(*(x.to(dev, non_blocking=True) for x in host_ids[i % B.N_BATCHES]))   # global loss
+        pinned[i & 1].copy_(out, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        if prev is not None:                      # read every step's loss on the host, one step behind
+            prev[0].synchronize()
+            last = prev[1].clone()
+        prev = (ev, pinned[i & 1])
+    prev[0].synchronize()
+    last = prev[1].clone()
     e1.record()
     barrier()
     t1 = time.time()

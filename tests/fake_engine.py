@@ -50,6 +50,37 @@ class FakeEngine:
         return (torch.from_numpy(np.bincount(owner, minlength=world).astype(np.int32)),
                 torch.from_numpy((a // world)[order].astype(np.int32)), torch.from_numpy(slot))
 
+    def owner_bucket_combined(self, ids, n_user, total_users, world):
+        a = ids.numpy()
+        owner = a % world
+        user_rows = (total_users - owner + world - 1) // world
+        local = a // world + np.where(np.arange(len(a)) >= n_user, user_rows, 0)
+        order = np.argsort(owner, kind="stable")
+        slot = np.empty(len(a), dtype=np.int32)
+        slot[order] = np.arange(len(a), dtype=np.int32)
+        return (torch.from_numpy(np.bincount(owner, minlength=world).astype(np.int32)),
+                torch.from_numpy(local[order].astype(np.int32)), torch.from_numpy(slot))
+
+    def pairwise_grad_rows(self, kind, rows, dim, uslot, pslot, nslot, inv_B, d_rows, out4, margin=0.5, c_loss=1.0,
+                           c_l2=1.0):
+        r = rows.numpy().astype(np.float64)
+        emb, bias = r[:, :dim], r[:, dim:dim + 1]
+        us, ps, ns = (t.numpy() for t in (uslot, pslot, nslot))
+        B = len(us)
+        if kind == 0:
+            loss, l2 = O.bpr_forward(emb, emb, bias, us, ps, ns)
+            gr = O.bpr_grads(emb, emb, bias, us, ps, ns, c_loss * B * inv_B, c_l2)
+            loss = loss * B * inv_B
+        else:
+            loss, l2 = O.ucml_forward(emb, emb, bias, us, ps, ns, margin)
+            gr = O.ucml_grads(emb, emb, bias, us, ps, ns, margin, c_loss, c_l2)
+        d = d_rows.numpy()
+        d[np.concatenate([us, ps, ns]), dim:] = 0.0
+        d[gr["user"][0], :dim] = gr["user"][1]
+        d[gr["item"][0], :dim] = gr["item"][1]
+        d[gr["bias"][0], dim] = gr["bias"][1].reshape(-1)
+        out4[0], out4[1] = float(loss), float(l2)
+
     def pairwise_grad_slots(self, kind, user_rows, item_rows, bias_rows, uslot, pslot, nslot, inv_B, d_user, d_item,
                             d_bias, out4, margin=0.5, c_loss=1.0, c_l2=1.0):
         u, i, b = (t.numpy().astype(np.float64) for t in (user_rows, item_rows, bias_rows))

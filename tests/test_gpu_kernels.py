@@ -444,3 +444,40 @@ def test_pairwise_grad_slots(eng, kind):
     ref_b[gr["bias"][0]] = gr["bias"][1].reshape(-1, 1)
     tol = 1e-4 if kind == "ucml" else ATOL
     close(du, ref_u, atol=tol), close(di, ref_i, atol=tol), close(db, ref_b, atol=tol)
+
+
+def test_owner_bucket_combined_and_grad_rows(eng):
+    """The combined-table form of the sharded step: (owner, combined local row) lookups and row-form gradients."""
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(10)
+    U, I, B, D, R = 1003, 2005, 400, 64, 3
+    uid, pid, nid = (rng.integers(0, n, B).astype(np.int32) for n in (U, I, I))
+    ids = np.concatenate([uid, pid, nid])
+    counts, send_local, slot = (t.cpu().numpy() for t in eng.owner_bucket_combined(dev(ids, torch.int32), B, U, R))
+    owner = ids % R
+    assert np.array_equal(counts, np.bincount(owner, minlength=R))
+    assert sorted(slot.tolist()) == list(range(3 * B))
+    user_rows = (U - owner + R - 1) // R
+    want_local = ids // R + np.where(np.arange(3 * B) >= B, user_rows, 0)
+    assert np.array_equal(send_local[slot], want_local)
+    assert np.array_equal(np.repeat(np.arange(R), counts)[slot], owner)
+    # gradients on fetched rows (width D+4, bias in column D)
+    W = D + 4
+    rows = np.zeros((3 * B, W))
+    rows[:, :D + 1] = rng.uniform(-0.05, 0.05, (3 * B, D + 1))
+    perm = rng.permutation(3 * B).astype(np.int32)
+    us, ps, ns = perm[:B], perm[B:2 * B], perm[2 * B:]
+    trows = dev(rows)
+    r64 = trows.cpu().numpy().astype(np.float64)
+    d_rows = torch.full_like(trows, 7.0)       # every touched entry must be overwritten (incl. the padding)
+    out4 = torch.zeros(4, device="cuda")
+    eng.pairwise_grad_rows(N.ORX_PAIR_BPR, trows, D, dev(us, torch.int32), dev(ps, torch.int32), dev(ns, torch.int32),
+                           1.0 / (B * R), d_rows, out4, 0.5, 1.0, 1.0)
+    emb, bias = r64[:, :D], r64[:, D:D + 1]
+    loss, l2 = O.bpr_forward(emb, emb, bias, us, ps, ns)
+    gr = O.bpr_grads(emb, emb, bias, us, ps, ns, 1.0 / R, 1.0)
+    ref = np.zeros_like(r64)
+    ref[gr["user"][0], :D], ref[gr["item"][0], :D] = gr["user"][1], gr["item"][1]
+    ref[gr["bias"][0], D] = gr["bias"][1].reshape(-1)
+    close(out4[0], loss / R, rtol=2e-5), close(out4[1], l2, rtol=2e-5)
+    close(d_rows, ref)
