@@ -44,8 +44,8 @@ struct ChunkMeta {  // per-lane: triplet (chunk*CH + lane), lanes < CH
   int u, p, n, du, dp, dn, fl;
 };
 
-template <int KIND, int OPT, int D, int STAGES>
-__global__ void __launch_bounds__(256, 1) k_pair_fused(const FusedArgs fa) {
+template <int KIND, int OPT, int D, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa) {
   constexpr int CH = 16;
   constexpr int K = D / 128;  // float4 per lane per row (D = 128 or 256)
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256, 1) k_pair_fused(const FusedArgs fa) {
     cp_wait<0>();
   }
 
-  __shared__ float sred[8][2];
+  __shared__ float sred[WARPS][2];
   __shared__ double sdbl[2][256];
   loss_acc = orx_group_sum<32>(loss_acc);
   l2_acc = orx_group_sum<32>(l2_acc);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256, 1) k_pair_fused(const FusedArgs fa) {
   if (threadIdx.x == 0) {
     float l = 0.f, q = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < WARPS; ++w) {
       l += sred[w][0];
       q += sred[w][1];
     }
@@ -352,12 +352,14 @@ __global__ void __launch_bounds__(256, 1) k_pair_fused(const FusedArgs fa) {
     }
     if (blockIdx.x == 0) {
       double l = 0.0, q = 0.0;
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
-        l += (double)__ldcg(a.partials + 2 * i);
-        q += (double)__ldcg(a.partials + 2 * i + 1);
+      if (threadIdx.x < 256) {
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) {
+          l += (double)__ldcg(a.partials + 2 * i);
+          q += (double)__ldcg(a.partials + 2 * i + 1);
+        }
+        sdbl[0][threadIdx.x] = l;
+        sdbl[1][threadIdx.x] = q;
       }
-      sdbl[0][threadIdx.x] = l;
-      sdbl[1][threadIdx.x] = q;
       __syncthreads();
       for (int s = 128; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
@@ -383,18 +385,18 @@ __global__ void __launch_bounds__(256, 1) k_pair_fused(const FusedArgs fa) {
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-template <int KIND, int OPT, int D, int STAGES>
+template <int KIND, int OPT, int D, int STAGES, int WARPS>
 static int launch_fused(orx_ctx* c, FusedArgs& fa, cudaStream_t st) {
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   constexpr int NR = 3 + (S0 ? 3 : 0) + (S1 ? 3 : 0);
-  const size_t smem = (size_t)8 * STAGES * (NR * (D / 128) * 512 + 32);
-  auto kern = k_pair_fused<KIND, OPT, D, STAGES>;
+  const size_t smem = (size_t)WARPS * STAGES * (NR * (D / 128) * 512 + 32);
+  auto kern = k_pair_fused<KIND, OPT, D, STAGES, WARPS>;
   static bool configured = false;
   if (!configured) {
     ORX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    ORX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    ORX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     if (per_sm < 1) {
       orx_set_error("k_pair_fused does not fit on an SM (smem %zu)", smem);
       return ORX_ERR_UNSUPPORTED;
@@ -402,12 +404,12 @@ static int launch_fused(orx_ctx* c, FusedArgs& fa, cudaStream_t st) {
     configured = true;
   }
   void* args[] = {(void*)&fa};
-  ORX_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(c->num_sms), dim3(256), args, smem, st));
+  ORX_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(c->num_sms), dim3(WARPS * 32), args, smem, st));
   return ORX_OK;
 }
 
 // Returns ORX_ERR_UNSUPPORTED when this (kind, optimizer, dim) has no fused instance: the caller then uses
-// the three-launch path.
+// the three-launch path.  ORX_FUSED_CFG = "<warps>x<stages>" picks the tuning point (default 16x4).
 int orx_launch_pair_fused(orx_ctx* c, int kind, int opt_kind, PairArgs& pa, float loss_scale, float* out4,
                           cudaStream_t st) {
   if (pa.D != 128 || opt_kind == ORX_OPT_ADAM_DENSE || opt_kind == ORX_OPT_ADAM_LAZY) return ORX_ERR_UNSUPPORTED;
@@ -418,16 +420,21 @@ int orx_launch_pair_fused(orx_ctx* c, int kind, int opt_kind, PairArgs& pa, floa
   fa.loss_scale = loss_scale;
   fa.n_chunks = (pa.B + 15) / 16;
   fa.p.partials = c->partials;
-  static int stages = -1;
-  if (stages < 0) {
-    const char* e = getenv("ORX_FUSED_STAGES");
-    stages = e ? atoi(e) : 8;
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("ORX_FUSED_CFG");
+    int w = 16, s = 4;
+    if (e) sscanf(e, "%dx%d", &w, &s);
+    cfg = w * 100 + s;
   }
-#define ORX_FUSED_CASE(KIND, OPT)                                                       \
-  switch (stages) {                                                                      \
-    case 4: return launch_fused<KIND, OPT, 128, 4>(c, fa, st);                           \
-    case 6: return launch_fused<KIND, OPT, 128, 6>(c, fa, st);                           \
-    default: return launch_fused<KIND, OPT, 128, 8>(c, fa, st);                          \
+#define ORX_FUSED_CASE(KIND, OPT)                                                         \
+  switch (cfg) {                                                                           \
+    case 808: return launch_fused<KIND, OPT, 128, 8, 8>(c, fa, st);                        \
+    case 1603: return launch_fused<KIND, OPT, 128, 3, 16>(c, fa, st);                      \
+    case 2402: return launch_fused<KIND, OPT, 128, 2, 24>(c, fa, st);                      \
+    case 2403: return launch_fused<KIND, OPT, 128, 3, 24>(c, fa, st);                      \
+    case 3202: return launch_fused<KIND, OPT, 128, 2, 32>(c, fa, st);                      \
+    default: return launch_fused<KIND, OPT, 128, 4, 16>(c, fa, st);                        \
   }
   if (kind == ORX_PAIR_BPR) {
     if (opt_kind == ORX_OPT_SGD) { ORX_FUSED_CASE(ORX_PAIR_BPR, ORX_OPT_SGD) }

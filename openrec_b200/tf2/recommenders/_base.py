@@ -23,6 +23,9 @@ def ids_any(x):
     """-> (int32 ids, on_host).  Host data (numpy / CPU tensors) stays on the host in pinned memory so the
     fused step can take it through the C-ABI's host-buffer entry point (one call: H2D + kernels + D2H)."""
     from ...tfshim import core
+    if type(x) is torch.Tensor and x.dtype == torch.int32 and x.dim() == 1 and not x.is_cuda and x.is_pinned() \
+            and core.device().type == "cuda":
+        return x, True                       # fast path: already a pinned int32 host batch
     if isinstance(x, (core.Tensor, core.Variable)):
         t = x.t
     elif torch.is_tensor(x):
@@ -62,10 +65,15 @@ class FusedRecommender(Model):
     """Base: subclasses define the kernels behind _orx_forward / _orx_run_step / _orx_run_grad."""
 
     def _tables(self, optimizer=None):
-        vs = (self.user_latent_factor.embeddings, self.item_latent_factor.embeddings, self.item_bias.embeddings)
-        if optimizer is None:
-            return tuple(N.table(v.t) for v in vs)
-        return tuple(optimizer.table(v) for v in vs)
+        """orx_table_t structs of (user, item, bias); cached per optimizer (pointers never change)."""
+        cache = self.__dict__.setdefault("_orx_cache_tables", {})
+        key = id(optimizer)
+        t = cache.get(key)
+        if t is None:
+            vs = (self.user_latent_factor.embeddings, self.item_latent_factor.embeddings, self.item_bias.embeddings)
+            t = cache[key] = tuple(N.table(v.t) for v in vs) if optimizer is None else \
+                tuple(optimizer.table(v) for v in vs)
+        return t
 
     def _orx_step_variables(self):
         return self.trainable_variables

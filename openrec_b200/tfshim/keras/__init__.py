@@ -16,7 +16,7 @@ class Sequential(Model):
         self.layers = list(layers or [])
 
     def add(self, layer):
-        self.layers.append(layer)
+        self.layers = self.layers + [layer]   # reassign: invalidates cached variable lists
 
     def build(self, in_dim):
         for l in self.layers:

@@ -21,10 +21,18 @@ def set_seed(seed):
     _seed = itertools.count(int(seed))
 
 
+_VERSION = [0]   # bumped whenever any layer attribute is (re)assigned: invalidates the cached variable lists
+
+
 class Layer:
     def __init__(self, name=None, trainable=True, **kwargs):
         self.name = name or type(self).__name__.lower()
         self.trainable = trainable
+
+    def __setattr__(self, key, value):
+        if not key.startswith("_orx_cache"):
+            _VERSION[0] += 1
+        object.__setattr__(self, key, value)
 
     def __call__(self, *args, **kwargs):
         return self.call(*args, **kwargs)
@@ -45,12 +53,16 @@ class Layer:
 
     @property
     def variables(self):
+        cache = self.__dict__.get("_orx_cache_vars")
+        if cache is not None and cache[0] == _VERSION[0]:
+            return list(cache[1])
         out, seen = [], set()
         for v in self._own_variables() + [w for s in self._sublayers() for w in s.variables]:
             if id(v) not in seen:
                 seen.add(id(v))
                 out.append(v)
-        return out
+        self._orx_cache_vars = (_VERSION[0], out)
+        return list(out)
 
     @property
     def trainable_variables(self):
