@@ -4,6 +4,8 @@
 //
 // Reference path: openrec/tf2/recommenders/dlrm.py:63-100, modules/multi_layer_perceptron.py:5-18,
 // modules/second_order_feature_interaction.py:12-34.
+#include <stdlib.h>
+
 #include "orx_common.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -220,9 +222,26 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int64
   }
 }
 
+int orx_launch_gemm_tc(int TA, int TB, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc,
+                       int M, int N, int K, const float* bias, int act, cudaStream_t st);   // orx_mlp_tc.cu
+
+// ORX_MLP_SIMT=1 forces the fp32 SIMT tiles (the reference the tcgen05 path is checked against in the tests)
+static bool mlp_use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ORX_MLP_SIMT");
+    v = (e && atoi(e)) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 template <int TA, int TB>
 static int launch_gemm(const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N,
                        int K, const float* bias, int act, cudaStream_t st) {
+  if (mlp_use_tc()) {   // tensor cores (tcgen05, 3xTF32) whenever the shape fills a tile reasonably
+    const int rc = orx_launch_gemm_tc(TA, TB, A, lda, Bm, ldb, C, ldc, M, N, K, bias, act, st);
+    if (rc != ORX_ERR_UNSUPPORTED) return rc;
+  }
   dim3 grid((N + 63) / 64, (M + 63) / 64);
   k_gemm<TA, TB><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, C, ldc, M, N, K, bias, act);
   ORX_LAUNCH_CHECK();

@@ -24,7 +24,15 @@ struct FusedArgs {
   float* out4;
   float loss_scale;
   int n_chunks;
+  unsigned long long* dbg;  // optional [16]: globaltimer stamps of block 0 / last-finishing warp (ORX_FUSED_DBG)
 };
+
+__device__ __forceinline__ unsigned long long orx_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ORX_STAMP(i) do { if (fa.dbg && blockIdx.x == 0 && threadIdx.x == 0) fa.dbg[i] = orx_gtime(); } while (0)
 
 __device__ __forceinline__ void cp16(void* smem_dst, const float* gsrc, bool pred) {
   const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -60,6 +68,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
 
+  ORX_STAMP(0);
   // ------------------------------------------------------------------ phase A: batch index
   // Four independent ids per thread: first-slot loads, then claims (CAS) are issued back to back so their L2
   // round trips overlap; anything that did not claim an empty slot at once takes the general insert.
@@ -100,7 +109,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
         if (live[q]) orx_hash_insert(isu[q] ? a.hu : a.hi, id[q], 0);
     }
   }
+  ORX_STAMP(1);
   grid.sync();
+  ORX_STAMP(2);
   const int n_su = fa.counters[0], n_si = fa.counters[1], n_bad = fa.counters[3];  // final after phase A
 
   // ------------------------------------------------------------------ phase B: persistent gather-score-update
@@ -297,6 +308,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
     }
     cp_wait<0>();
   }
+  ORX_STAMP(3);
+  if (fa.dbg && lane == 0) atomicMax(fa.dbg + 8, orx_gtime());   // when the LAST warp of the grid left phase B
 
   __shared__ float sred[WARPS][2];
   __shared__ double sdbl[2][256];
@@ -318,6 +331,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
     a.partials[2 * blockIdx.x + 1] = q;
   }
   grid.sync();
+  ORX_STAMP(4);
 
   // ------------------------------------------------------------------ phase C: staged rows, loss, reset
   {
@@ -380,6 +394,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
       }
     }
   }
+  ORX_STAMP(5);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -403,8 +418,28 @@ static int launch_fused(orx_ctx* c, FusedArgs& fa, cudaStream_t st) {
     }
     configured = true;
   }
+  static unsigned long long* dbg = nullptr;
+  static int dbg_on = -1, dbg_left = 0;
+  if (dbg_on < 0) {
+    dbg_on = getenv("ORX_FUSED_DBG") ? 1 : 0;
+    if (dbg_on) {
+      ORX_CUDA(cudaMalloc(&dbg, 16 * sizeof(unsigned long long)));
+      dbg_left = 40;
+    }
+  }
+  fa.dbg = (dbg_on && dbg_left > 0) ? dbg : nullptr;
+  if (fa.dbg) ORX_CUDA(cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), st));
   void* args[] = {(void*)&fa};
   ORX_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(c->num_sms), dim3(WARPS * 32), args, smem, st));
+  if (fa.dbg) {
+    unsigned long long h[16];
+    ORX_CUDA(cudaStreamSynchronize(st));
+    ORX_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    if (--dbg_left < 5)
+      fprintf(stderr, "[orx fused dbg] A %.1f us | sync %.1f | B(block0) %.1f  B(last warp) %.1f | sync %.1f | C %.1f | total %.1f\n",
+              (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[8] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3,
+              (h[5] - h[4]) * 1e-3, (h[5] - h[0]) * 1e-3);
+  }
   return ORX_OK;
 }
 

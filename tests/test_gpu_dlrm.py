@@ -28,7 +28,9 @@ def close(t, ref, atol=1e-5, rtol=1e-5):
     np.testing.assert_allclose(got, np.asarray(ref, dtype=np.float64).reshape(got.shape), atol=atol, rtol=rtol)
 
 
-@pytest.mark.parametrize("B,inn,out,act", [(37, 13, 8, 1), (300, 479, 96, 2), (1000, 64, 1, 0), (129, 5, 130, 1)])
+@pytest.mark.parametrize("B,inn,out,act", [(37, 13, 8, 1), (300, 479, 96, 2), (1000, 64, 1, 0), (129, 5, 130, 1),
+                                            (512, 256, 128, 1), (1111, 479, 1024, 1), (4096, 512, 256, 0),
+                                            (200, 13, 512, 1), (777, 1024, 64, 2)])
 def test_mlp_layer_fwd_bwd(B, inn, out, act):
     from openrec_b200 import native as N
     eng = N.engine()
