@@ -270,6 +270,22 @@ def bench_single(args, eng, dev, barrier):
     eng.profile_enable(False)
     loss_check = out4.cpu().numpy().tolist()
 
+    # ---- secondary workloads on the same tables (BASELINE configs[2] UCML; SGD variant), short loops
+    def timed(kind, o, n=min(K, 300)):
+        for i in range(5):
+            u, p, q = dev_ids[i % N_BATCHES]
+            eng.pairwise_step(kind, *tabs, u, p, q, o, out4)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            u, p, q = dev_ids[i % N_BATCHES]
+            eng.pairwise_step(kind, *tabs, u, p, q, o, out4)
+        e1.record()
+        torch.cuda.synchronize()
+        return n * B / (e0.elapsed_time(e1) * 1e-3)
+    secondary = {"ucml_adagrad_triplets_per_sec": timed(N.ORX_PAIR_UCML, opt),
+                 "bpr_sgd_triplets_per_sec": timed(N.ORX_PAIR_BPR, N.opt(N.ORX_OPT_SGD, LR))}
+
     # ---- e2e: public API (openrec.tf2 BPR + GradientTape + Adagrad), host ids in, loss out, every step
     sys.path.insert(0, os.path.join(ROOT, "compat"))
     import tensorflow as tf
@@ -324,7 +340,7 @@ def bench_single(args, eng, dev, barrier):
               "roofline": roofline,
               "e2e_api": "openrec.tf2.recommenders.BPR + tf.GradientTape + tf.keras.optimizers.Adagrad (shim); "
                          "pinned host ids in, loss read to host each step",
-              "extra": {"last_loss_value_path": loss_check[:2], "last_loss_e2e": last}}
+              "extra": {"last_loss_value_path": loss_check[:2], "last_loss_e2e": last, **secondary}}
     if not args.no_cpu:
         v, ms, done, info = cpu_arm(50, 2, float(os.environ.get("ORX_CPU_BUDGET_S", "20")))
         result["cpu_baseline"] = {"value": v, "unit": UNIT, **info}

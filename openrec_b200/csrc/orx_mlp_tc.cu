@@ -65,10 +65,17 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // smem byte offset of element (row r, k) inside one K-major no-swizzle operand tile
 __device__ __forceinline__ int tile_off(int r, int k) { return (r >> 3) * ((BK / 4) * 128) + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4; }
 
+// hi = TF32(v) and lo = TF32(v - hi), both rounded to nearest (cvt.rna): truncation would bias every product
+// the same way and the error would grow linearly with K instead of with sqrt(K).
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float v, float* hi, float* lo) {
-  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  const float h = to_tf32(v);
   *hi = h;
-  *lo = __uint_as_float(__float_as_uint(v - h) & 0xffffe000u);
+  *lo = to_tf32(v - h);
 }
 
 // A tile source: TA=0 -> A[m*lda + k] (row-major [M,K]); TA=1 -> A[k*lda + m] ([K,M] row-major).

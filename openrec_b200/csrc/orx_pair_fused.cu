@@ -5,9 +5,9 @@
 // this part (tools/randrow_bw.cu): with 8 triplets per short-lived warp the load pipeline never left its
 // prologue.  Here one CTA per SM stays resident for the whole step:
 //   phase A  batch index (hash inserts, several independent ids per thread)            | grid.sync
-//   phase B  persistent warps fetch 16-triplet chunks from an atomic work counter; the rows of the next STAGES
-//            triplets are always in flight in a per-warp shared-memory ring (cp.async / LDGSTS), and the ring keeps
-//            running ACROSS chunk boundaries (the next chunk's ids and hash probes are prefetched)    | grid.sync
+//   phase B  every warp owns an equal, static range of triplets; the rows of its next STAGES triplets are always
+//            in flight in a per-warp shared-memory ring (cp.async / LDGSTS); the first rows are issued before the sync
+//            (equal static partition of the triplets over all warps of the grid)                        | grid.sync
 //   phase C  optimizer for the staged (shared) rows, staging re-zeroed, deterministic loss reduction, counters reset
 // Semantics are exactly those of orx_pairwise.cu's three-launch path (same staging rule, same math).
 #include <cooperative_groups.h>
@@ -54,13 +54,12 @@ struct ChunkMeta {  // per-lane: triplet (chunk*CH + lane), lanes < CH
 
 template <int KIND, int OPT, int D, int STAGES, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa) {
-  constexpr int CH = 16;
   constexpr int K = D / 128;  // float4 per lane per row (D = 128 or 256)
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   constexpr int NR = 3 + (S0 ? 3 : 0) + (S1 ? 3 : 0);
   constexpr int STAGE_BYTES = NR * K * 512 + 32;  // rows + {bp, bn, bps0, bns0, bps1, bns1, -, -}
-  static_assert(STAGES >= 2 && STAGES <= CH, "bad ring depth");
+  static_assert(STAGES >= 2 && STAGES <= 8, "bad ring depth");
   extern __shared__ __align__(16) unsigned char orx_smem[];
   const PairArgs& a = fa.p;
   cg::grid_group grid = cg::this_grid();
@@ -68,6 +67,40 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
 
+  unsigned char* wring = orx_smem + (size_t)wib * STAGES * STAGE_BYTES;
+  auto row_slot = [&](int stage, int row, int k) -> float4* {
+    return reinterpret_cast<float4*>(wring + (size_t)stage * STAGE_BYTES) + (row * K + k) * 32 + lane;
+  };
+  auto mini = [&](int stage) -> float* {
+    return reinterpret_cast<float*>(wring + (size_t)stage * STAGE_BYTES + NR * K * 512);
+  };
+  auto load_ids_at = [&](int c0, int cnt, ChunkMeta& m) {   // triplets c0 .. c0+cnt-1, one per lane
+    m.u = m.p = m.n = 0;
+    m.du = m.dp = m.dn = -1;
+    m.fl = 0;
+    if (lane < cnt) {
+      const int t = c0 + lane;
+      m.u = a.uid[t];
+      m.p = a.pid[t];
+      m.n = a.nid[t];
+      m.fl = (m.u >= 0 && m.u < a.rowsU && m.p >= 0 && m.p < a.rowsI && m.n >= 0 && m.n < a.rowsI) ? 1 : 0;
+    }
+  };
+  // put the variable rows of triplet j of metadata m in flight into ring slot `stage` (needs ids only)
+  auto issue_var = [&](const ChunkMeta& m, int j, int stage) {
+    const bool v = __shfl_sync(ORX_FULL, m.fl, j) & 1;
+    const int uu = __shfl_sync(ORX_FULL, m.u, j), pp = __shfl_sync(ORX_FULL, m.p, j), nn = __shfl_sync(ORX_FULL, m.n, j);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int off = (k * 32 + lane) * 4;
+      cp16(row_slot(stage, 0, k), v ? a.U + (int64_t)uu * D + off : a.U, v);
+      cp16(row_slot(stage, 1, k), v ? a.I + (int64_t)pp * D + off : a.I, v);
+      cp16(row_slot(stage, 2, k), v ? a.I + (int64_t)nn * D + off : a.I, v);
+    }
+    float* ms = mini(stage);
+    if (lane == 0) cp4(ms + 0, v ? a.Bv + pp : a.Bv, v);
+    if (lane == 1) cp4(ms + 1, v ? a.Bv + nn : a.Bv, v);
+  };
   ORX_STAMP(0);
   // ------------------------------------------------------------------ phase A: batch index
   // Four independent ids per thread: first-slot loads, then claims (CAS) are issued back to back so their L2
@@ -109,37 +142,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
         if (live[q]) orx_hash_insert(isu[q] ? a.hu : a.hi, id[q], 0);
     }
   }
+  // this warp's own triplet range is static, so its first rows can already travel while the grid synchronises
+  const int nw_total = gridDim.x * WARPS;
+  const int T = (a.B + nw_total - 1) / nw_total;
+  const int t_begin = min(a.B, (blockIdx.x * WARPS + wib) * T), t_end = min(a.B, t_begin + T);
+  ChunkMeta m_first;
+  load_ids_at(t_begin, min(32, t_end - t_begin), m_first);
+#pragma unroll
+  for (int j = 0; j < STAGES; ++j) issue_var(m_first, j, j);
   ORX_STAMP(1);
   grid.sync();
   ORX_STAMP(2);
   const int n_su = fa.counters[0], n_si = fa.counters[1], n_bad = fa.counters[3];  // final after phase A
 
   // ------------------------------------------------------------------ phase B: persistent gather-score-update
-  unsigned char* wring = orx_smem + (size_t)wib * STAGES * STAGE_BYTES;
-  auto row_slot = [&](int stage, int row, int k) -> float4* {
-    return reinterpret_cast<float4*>(wring + (size_t)stage * STAGE_BYTES) + (row * K + k) * 32 + lane;
-  };
-  auto mini = [&](int stage) -> float* {
-    return reinterpret_cast<float*>(wring + (size_t)stage * STAGE_BYTES + NR * K * 512);
-  };
-  auto fetch = [&]() -> int {
-    int c = 0;
-    if (lane == 0) c = atomicAdd(fa.counters + 5, 1);
-    c = __shfl_sync(ORX_FULL, c, 0);
-    return c < fa.n_chunks ? c : -1;
-  };
-  auto load_ids = [&](int chunk, ChunkMeta& m) {
-    m.u = m.p = m.n = 0;
-    m.du = m.dp = m.dn = -1;
-    m.fl = 0;
-    const int t = chunk * CH + lane;
-    if (chunk >= 0 && lane < CH && t < a.B) {
-      m.u = a.uid[t];
-      m.p = a.pid[t];
-      m.n = a.nid[t];
-      m.fl = (m.u >= 0 && m.u < a.rowsU && m.p >= 0 && m.p < a.rowsI && m.n >= 0 && m.n < a.rowsI) ? 1 : 0;
-    }
-  };
   auto probe = [&](ChunkMeta& m) {
     if (m.fl & 1) {
       const uint32_t cu = orx_hash_find(a.hu, m.u, &m.du);
@@ -148,34 +164,26 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
       m.fl |= (cu == 1u ? 2 : 0) | (cp == 1u ? 4 : 0) | (cn == 1u ? 8 : 0);
     }
   };
-  // put triplet j of chunk-metadata m in flight into ring slot `stage`
-  auto issue = [&](const ChunkMeta& m, int j, int stage) {
+  // optimizer-slot rows (+ bias slots) of the rows this triplet owns: needs the probe results
+  auto issue_slots = [&](const ChunkMeta& m, int j, int stage) {
+    if (!S0) return;
     const int fl = __shfl_sync(ORX_FULL, m.fl, j);
     const int uu = __shfl_sync(ORX_FULL, m.u, j), pp = __shfl_sync(ORX_FULL, m.p, j), nn = __shfl_sync(ORX_FULL, m.n, j);
-    const bool v = fl & 1;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int off = (k * 32 + lane) * 4;
-      cp16(row_slot(stage, 0, k), v ? a.U + (int64_t)uu * D + off : a.U, v);
-      cp16(row_slot(stage, 1, k), v ? a.I + (int64_t)pp * D + off : a.I, v);
-      cp16(row_slot(stage, 2, k), v ? a.I + (int64_t)nn * D + off : a.I, v);
-      if (S0) {
-        cp16(row_slot(stage, 3, k), (fl & 2) ? a.Us0 + (int64_t)uu * D + off : a.Us0, fl & 2);
-        cp16(row_slot(stage, 4, k), (fl & 4) ? a.Is0 + (int64_t)pp * D + off : a.Is0, fl & 4);
-        cp16(row_slot(stage, 5, k), (fl & 8) ? a.Is0 + (int64_t)nn * D + off : a.Is0, fl & 8);
-      }
+      cp16(row_slot(stage, 3, k), (fl & 2) ? a.Us0 + (int64_t)uu * D + off : a.Us0, fl & 2);
+      cp16(row_slot(stage, 4, k), (fl & 4) ? a.Is0 + (int64_t)pp * D + off : a.Is0, fl & 4);
+      cp16(row_slot(stage, 5, k), (fl & 8) ? a.Is0 + (int64_t)nn * D + off : a.Is0, fl & 8);
       if (S1) {
         cp16(row_slot(stage, 6, k), (fl & 2) ? a.Us1 + (int64_t)uu * D + off : a.Us1, fl & 2);
         cp16(row_slot(stage, 7, k), (fl & 4) ? a.Is1 + (int64_t)pp * D + off : a.Is1, fl & 4);
         cp16(row_slot(stage, 8, k), (fl & 8) ? a.Is1 + (int64_t)nn * D + off : a.Is1, fl & 8);
       }
     }
-    // item_bias scalars (+ their slots) ride along as 4-byte copies issued by lanes 0..5
     float* ms = mini(stage);
-    if (lane == 0) cp4(ms + 0, v ? a.Bv + pp : a.Bv, v);
-    if (lane == 1) cp4(ms + 1, v ? a.Bv + nn : a.Bv, v);
-    if (S0 && lane == 2) cp4(ms + 2, (fl & 4) ? a.Bs0 + pp : a.Bs0, fl & 4);
-    if (S0 && lane == 3) cp4(ms + 3, (fl & 8) ? a.Bs0 + nn : a.Bs0, fl & 8);
+    if (lane == 2) cp4(ms + 2, (fl & 4) ? a.Bs0 + pp : a.Bs0, fl & 4);
+    if (lane == 3) cp4(ms + 3, (fl & 8) ? a.Bs0 + nn : a.Bs0, fl & 8);
     if (S1 && lane == 4) cp4(ms + 4, (fl & 4) ? a.Bs1 + pp : a.Bs1, fl & 4);
     if (S1 && lane == 5) cp4(ms + 5, (fl & 8) ? a.Bs1 + nn : a.Bs1, fl & 8);
   };
@@ -267,46 +275,41 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pair_fused(const FusedArgs fa
     __syncwarp();  // every lane has read this stage (incl. the shared bias scalars) before it is refilled
   };
 
+  // static partition: every warp of the grid owns T consecutive triplets (equal work, no work counter);
+  // metadata for up to 32 of them lives in the lanes.
   {
-    ChunkMeta mc, mn;
-    int cur = fetch();
-    int nxt = fetch();
-    int nx2 = fetch();
-    load_ids(cur, mc);
-    load_ids(nxt, mn);
-    probe(mc);
+    bool first = true;
+    for (int c0 = t_begin; c0 < t_end; c0 += 32) {
+      const int cnt = min(32, t_end - c0);
+      ChunkMeta mc;
+      if (first) mc = m_first;               // ids loaded (and the first rows put in flight) before the grid sync
+      else load_ids_at(c0, cnt, mc);
+      if (!first) {
 #pragma unroll
-    for (int j = 0; j < STAGES; ++j) {
-      issue(mc, j, j);
-      cp_commit();
-    }
-    int ring = 0;
-    while (cur >= 0) {
-      bool next_probed = false;
+        for (int j = 0; j < STAGES; ++j) issue_var(mc, j, j);
+      }
+      probe(mc);
+#pragma unroll
+      for (int j = 0; j < STAGES; ++j) {
+        issue_slots(mc, j, j);
+        cp_commit();
+      }
+      first = false;
+      int ring = 0;
 #pragma unroll 1
-      for (int j = 0; j < CH; ++j) {
+      for (int j = 0; j < cnt; ++j) {
         cp_wait<STAGES - 1>();
         process(mc, j, ring);
-        const int t = j + STAGES;
-        if (t < CH) {
-          issue(mc, t, ring);
-        } else if (nxt >= 0) {
-          if (!next_probed) {
-            probe(mn);
-            next_probed = true;
-          }
-          issue(mn, t - CH, ring);
+        if (j + STAGES < cnt) {
+          issue_var(mc, j + STAGES, ring);
+          issue_slots(mc, j + STAGES, ring);
         }
-        cp_commit();  // one group per processed triplet (possibly empty) keeps wait_group<STAGES-1> exact
+        cp_commit();
         ring = ring + 1 == STAGES ? 0 : ring + 1;
       }
-      mc = mn;
-      cur = nxt;
-      nxt = nx2;
-      load_ids(nxt, mn);
-      nx2 = nxt >= 0 ? fetch() : -1;
+      cp_wait<0>();
     }
-    cp_wait<0>();
+    cp_wait<0>();   // (empty range: the zero-filled copies issued before the sync)
   }
   ORX_STAMP(3);
   if (fa.dbg && lane == 0) atomicMax(fa.dbg + 8, orx_gtime());   // when the LAST warp of the grid left phase B

@@ -119,7 +119,7 @@ def make_dlrm(rng):
     sparse = np.stack([rng.integers(0, n, B) for n in ln_emb], axis=1).astype(np.int32)
     label = (rng.random(B) < 0.3).astype(np.float32)
     for tag, kw in (("mse", {}), ("bce_self", dict(loss_func="bce", arch_interaction_itself=True)),
-                    ("clip", dict(loss_threshold=0.45))):
+                    ("clip", dict(loss_threshold=0.45)), ("bce", dict(loss_func="bce"))):
         torch.manual_seed(3)
         m = DLRM(m_spa=m_spa, ln_emb=ln_emb, ln_bot=ln_bot, ln_top=ln_top, **kw)
         loss = m(torch.tensor(dense), torch.tensor(sparse), torch.tensor(label, dtype=torch.float64))

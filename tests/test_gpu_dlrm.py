@@ -92,7 +92,7 @@ def _load_golden_into(model, g):
 
 
 @pytest.mark.parametrize("tag,kw", [("mse", {}), ("bce_self", dict(loss_func="bce", arch_interaction_itself=True)),
-                                    ("clip", dict(loss_threshold=0.45))])
+                                    ("clip", dict(loss_threshold=0.45)), ("bce", dict(loss_func="bce"))])
 def test_dlrm_model_matches_reference_golden(tf, golden_dir, tag, kw):
     from openrec.tf2.recommenders import DLRM
     g = dict(np.load(os.path.join(golden_dir, f"dlrm_{tag}.npz")))
@@ -103,16 +103,19 @@ def test_dlrm_model_matches_reference_golden(tf, golden_dir, tag, kw):
         loss = model(g["dense"].astype(np.float32), g["sparse"], g["label"])
     # 'bce_self': the self-interaction saturates the top sigmoid, and log(1 - p + 1e-7) at p -> 1 is only good to
     # ~1e-3 in float32 (the reference computes in float32 too; the golden is float64)
-    lt, gt = (2e-2, 2e-5) if tag == "bce_self" else (1e-5, 2e-6)
-    close(float(loss), g["loss"], atol=2e-6, rtol=lt)
+    saturated = tag == "bce_self"
+    close(float(loss), g["loss"], atol=2e-6, rtol=2e-3 if saturated else 1e-5)
     grads = tape.gradient(loss, tv)
     for k, (gr, v) in enumerate(zip(grads, tv)):
         ref = g[f"grad{k}"]
         if gr.indices is not None:
-            dense_g = torch.zeros(v.shape, device="cuda").index_add_(0, gr.indices.t.long(), gr.values.t)
-            close(dense_g, ref, atol=gt, rtol=lt)
+            got = torch.zeros(v.shape, device="cuda").index_add_(0, gr.indices.t.long(), gr.values.t).cpu().numpy()
         else:
-            close(gr.values.numpy(), ref, atol=gt, rtol=lt)
+            got = gr.values.numpy()
+        if saturated:   # 1 - p is not representable near p = 1 in float32: only a norm-wise comparison is meaningful
+            assert np.linalg.norm(got - ref) <= 5e-2 * np.linalg.norm(ref) + 1e-6
+        else:
+            close(got, ref, atol=2e-6)
 
 
 @pytest.mark.parametrize("optname,mode", [("adam", "reference"), ("sgd", "dlrm"), ("adagrad", "dlrm")])

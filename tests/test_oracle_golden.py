@@ -111,7 +111,7 @@ def test_interaction_bug_compatible(golden_dir):
 
 
 @pytest.mark.parametrize("tag,kw", [("mse", {}), ("bce_self", dict(loss_func="bce", self_interaction=True)),
-                                    ("clip", dict(loss_threshold=0.45))])
+                                    ("clip", dict(loss_threshold=0.45)), ("bce", dict(loss_func="bce"))])
 def test_dlrm_forward_backward(golden_dir, tag, kw):
     g = _load(golden_dir, f"dlrm_{tag}.npz")
     nv = int(g["n_vars"])
