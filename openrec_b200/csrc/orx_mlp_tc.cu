@@ -124,22 +124,31 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_
   }
 }
 
+// The tensor core accumulates in fp32 with truncation; over hundreds of accumulations that bias grows linearly
+// with K (measured 3e-4 abs at K=1024).  So a TMEM accumulator only ever sums GROUP_KB k-blocks (64 K-elements,
+// 24 MMAs); it is then drained with tcgen05.ld into fp32 REGISTERS (round-to-nearest adds, one output row per
+// thread).  Two TMEM accumulators alternate, so the drain of group g-1 overlaps the MMAs of group g.
+constexpr int GROUP_KB = 2;
+
 template <int TA, int TB>
 __global__ void __launch_bounds__(128, 1) k_gemm_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
                                                     int64_t ldb, float* __restrict__ C, int64_t ldc, int M, int N, int K,
                                                     const float* __restrict__ bias, int act) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t mbar[NSTAGE];
+  __shared__ __align__(8) uint64_t mbar[NSTAGE];   // smem stage free again (its MMAs finished)
+  __shared__ __align__(8) uint64_t accbar[2];      // TMEM accumulator buffer complete (its group's MMAs finished)
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
 
-  if (warp == 0) {   // TMEM: 128 fp32 accumulator columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+  if (warp == 0) {   // TMEM: 2 x 128 fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) mbar_init(&mbar[s], 1);
+    mbar_init(&accbar[0], 1);
+    mbar_init(&accbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -147,63 +156,85 @@ __global__ void __launch_bounds__(128, 1) k_gemm_tc(const float* __restrict__ A,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
 
+  float acc[BN];   // this thread's output row (m0 + 32*warp + lane), fp32 accumulation across groups
+#pragma unroll
+  for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+
+  // drain TMEM accumulator `buf` (group number g) into the register accumulators
+  auto drain = [&](int g) {
+    const int buf = g & 1;
+    mbar_wait(&accbar[buf], (g >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + c0);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+
   const int nkb = (K + BK - 1) / BK;
+  const int ngroups = (nkb + GROUP_KB - 1) / GROUP_KB;
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % NSTAGE;
+    const int g = kb / GROUP_KB;                 // accumulation group and its TMEM buffer
+    const bool g_first = (kb % GROUP_KB) == 0, g_last = (kb % GROUP_KB) == GROUP_KB - 1 || kb == nkb - 1;
     unsigned char* st = smem + (size_t)s * STAGE_BYTES;
-    // the MMAs that last read this stage (block kb - NSTAGE) must have completed
-    if (kb >= NSTAGE) mbar_wait(&mbar[s], ((kb / NSTAGE) - 1) & 1);
-    // A: rows along M;  TA=0 source [M,K] row-major, TA=1 source [K,M] row-major
+    if (kb >= NSTAGE) mbar_wait(&mbar[s], ((kb / NSTAGE) - 1) & 1);   // MMAs of block kb-NSTAGE are done with this stage
     stage_tile<TA>(A, lda, m0, kb * BK, M, K, st, st + TILE_BYTES);
-    // B: rows along N;  TB=1 source [N,K] row-major (k contiguous), TB=0 source [K,N] row-major
     stage_tile<(TB == 1 ? 0 : 1)>(Bm, ldb, n0, kb * BK, N, K, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+    // group g reuses the TMEM buffer of group g-2: every thread must have drained g-2 before its first MMA.
+    // (the drain of g-2 ran after group g-1's first block was issued, i.e. earlier in program order)
     __syncthreads();
     if (threadIdx.x == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+      const uint32_t d = tmem_d + (uint32_t)((g & 1) * BN);
 #pragma unroll
       for (int ks = 0; ks < BK / 8; ++ks) {           // one MMA consumes K = 8 (two 16-byte core matrices = 256 B)
         const uint32_t o = ks * 256;
-        mma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_hi + o), (kb | ks) ? 1u : 0u);
-        mma_tf32(tmem_d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
-        mma_tf32(tmem_d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
+        mma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), (g_first && ks == 0) ? 0u : 1u);
+        mma_tf32(d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
+        mma_tf32(d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
       }
-      umma_commit(&mbar[s]);   // arrives when every MMA issued so far has finished reading smem / writing TMEM
+      umma_commit(&mbar[s]);                 // stage s may be overwritten once these MMAs are done
+      if (g_last) umma_commit(&accbar[g & 1]);   // ... and the group's accumulator is complete
     }
+    // overlap: while group g's MMAs run, fold the previous group's accumulator into the registers
+    if (g_first && g >= 1) drain(g - 1);
   }
-  // all MMAs done: the last commit covers everything issued before it
-  {
-    const int last = nkb - 1;
-    mbar_wait(&mbar[last % NSTAGE], (last / NSTAGE) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  }
-  // epilogue: warp w owns TMEM lanes [32w, 32w+32) = rows m0 + 32w + lane
+  drain(ngroups - 1);
+
+  // epilogue from registers: thread = one row
   const int m = m0 + warp * 32 + lane;
-#pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 8) {
-    uint32_t v[8];
-    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (m < M) {
+  if (m < M) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = n0 + c0 + j;
-        if (n < N) {
-          float x = __uint_as_float(v[j]) + (bias ? bias[n] : 0.f);
-          if (act == 1) x = fmaxf(x, 0.f);
-          else if (act == 2) x = orx_sigmoid(x);
-          C[(int64_t)m * ldc + n] = x;
-        }
+    for (int j = 0; j < BN; ++j) {
+      const int n = n0 + j;
+      if (n < N) {
+        float x = acc[j] + (bias ? bias[n] : 0.f);
+        if (act == 1) x = fmaxf(x, 0.f);
+        else if (act == 2) x = orx_sigmoid(x);
+        C[(int64_t)m * ldc + n] = x;
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_d) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_d) : "memory");
 }
 
 }  // namespace
