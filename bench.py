@@ -47,7 +47,8 @@ def workload_name(n_gpus):
     s = (f"BPR {U} users x {I} items, dim {D}, batch {B} per GPU, Adagrad lr {LR} (acc init 0.1), "
          f"ids uniform i.i.d. int32, {N_BATCHES} rotating id batches")
     if n_gpus > 1:
-        s += f", tables row-sharded over {n_gpus} GPUs (row r on rank r % N), NCCL all-to-all exchange"
+        s += (f", 1M users + 12.5M items per GPU row-sharded over {n_gpus} GPUs (row r on rank r % N), rows gathered and "
+              "gradients pushed over NVLink peer memory")
     return s
 
 
@@ -188,6 +189,7 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's "NCCL version ..." banner goes to stdout; the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     eng = N.engine(dev)
 

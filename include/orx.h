@@ -183,6 +183,32 @@ ORX_API int orx_pairwise_grad_rows(orx_handle_t h, int32_t kind, const float* ro
                                    float margin, float c_loss, float c_l2, float inv_B, float* d_rows, float* out4,
                                    orx_stream_t s);
 
+/* ---- one-sided (peer-memory) sharded step over NVLink: no NCCL in the data path (openrec_b200/sharded_peer.py) ----
+ * orx_peer_alloc/open/close/free: cudaMalloc + CUDA IPC handle (64 bytes) so every rank can map every other rank's
+ *   shard and inbox.
+ * orx_peer_t: device arrays (one entry per rank) of the mapped pointers.
+ * orx_peer_pairwise_push: bucket positions of this rank's 3B lookups, per-owner counts published to the owners,
+ *   then ONE kernel that gathers u/p/n rows from the owners with peer loads, scores, and pushes gradient rows +
+ *   combined local row ids into the owners' inboxes with peer stores.  pos_scratch: int32[3B].
+ * orx_peer_apply: the owner deduplicates all ranks' lookups found in its inbox and applies the optimizer once per
+ *   unique row.  The caller places a cross-rank barrier before push (shards final) and between push and apply. */
+typedef struct {
+  int32_t world, rank, dim, _pad;
+  int64_t total_users, total_items, cap;      /* cap: inbox capacity per source rank, >= 3*B */
+  void *emb, *bias, *inbox_emb, *inbox_bias, *inbox_ids, *inbox_cnt;   /* DEVICE arrays of `world` pointers */
+} orx_peer_t;
+ORX_API int orx_peer_alloc(orx_handle_t h, int64_t bytes, void** dev_ptr_out, uint8_t* handle_out64);
+ORX_API int orx_peer_open(orx_handle_t h, const uint8_t* handle64, void** dev_ptr_out);
+ORX_API int orx_peer_close(orx_handle_t h, void* dev_ptr);
+ORX_API int orx_peer_free(orx_handle_t h, void* dev_ptr);
+ORX_API int orx_peer_pairwise_push(orx_handle_t h, int32_t kind, const void* peer_host /* orx_peer_t* */,
+                                   const int32_t* uid, const int32_t* pid, const int32_t* nid, int32_t B,
+                                   int32_t* pos_scratch, float margin, float c_loss, float c_l2, float inv_B,
+                                   float* out4, orx_stream_t s);
+ORX_API int orx_peer_apply(orx_handle_t h, const orx_table_t* emb, const orx_table_t* bias, const int32_t* inbox_ids,
+                           const float* inbox_emb, const float* inbox_bias, const int32_t* inbox_cnt, int32_t world,
+                           int64_t cap, const orx_opt_t* opt_host, orx_stream_t s);
+
 /* ---- dense variables (GMF w, MLP kernels/biases): Keras dense apply ---------------------- */
 ORX_API int orx_dense_apply(orx_handle_t h, float* var, float* s0, float* s1, const float* grad, int64_t n,
                     const orx_opt_t* opt_host, orx_stream_t s);

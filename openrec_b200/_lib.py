@@ -28,6 +28,13 @@ class OrxTable(C.Structure):
                 ("dim", C.c_int32)]
 
 
+class OrxPeer(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("dim", C.c_int32), ("_pad", C.c_int32),
+                ("total_users", C.c_int64), ("total_items", C.c_int64), ("cap", C.c_int64),
+                ("emb", C.c_void_p), ("bias", C.c_void_p), ("inbox_emb", C.c_void_p), ("inbox_bias", C.c_void_p),
+                ("inbox_ids", C.c_void_p), ("inbox_cnt", C.c_void_p)]
+
+
 _vp, _i32, _i64, _f, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 _T = C.POINTER(OrxTable)
 _O = C.POINTER(OrxOpt)
@@ -60,6 +67,12 @@ SIGNATURES = {
     "orx_interact_bwd": [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _i64,
                          _vp],
     "orx_pred_loss": [_vp, _vp, _vp, _i32, _i32, _f, _vp, _vp, _vp, _vp],
+    "orx_peer_alloc": [_vp, _i64, C.POINTER(_vp), C.c_char_p],
+    "orx_peer_open": [_vp, C.c_char_p, C.POINTER(_vp)],
+    "orx_peer_close": [_vp, _vp],
+    "orx_peer_free": [_vp, _vp],
+    "orx_peer_pairwise_push": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _f, _f, _f, _f, _vp, _vp],
+    "orx_peer_apply": [_vp, _T, _T, _vp, _vp, _vp, _vp, _i32, _i64, _O, _vp],
     "orx_owner_bucket_combined": [_vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
     "orx_pairwise_grad_rows": [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _f, _f, _f, _f, _vp, _vp, _vp],
     "orx_owner_bucket": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],

@@ -129,7 +129,12 @@ def bench(args, rank, world, eng, barrier):
     K, W = args.steps, max(3, args.warmup)
     dev = eng.device
     U, I, D, Bsz = B.U, 12_500_000 * world, B.D, B.B      # BASELINE configs[4]: 100M items x 128 over 8 GPUs
-    model = ShardedPairwise(eng, rank, world, U, I, D, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
+    use_peer = os.environ.get("ORX_SHARDED", "peer") != "nccl"
+    if use_peer:   # one-sided NVLink peer-memory step (sharded_peer.py); ORX_SHARDED=nccl selects the all-to-all path
+        from .sharded_peer import PeerShardedPairwise
+        model = PeerShardedPairwise(eng, rank, world, U, I, D, Bsz, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
+    else:
+        model = ShardedPairwise(eng, rank, world, U, I, D, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     host_ids = [tuple(torch.randint(0, n, (Bsz,), generator=g, dtype=torch.int32).pin_memory() for n in (U, I, I))
                 for _ in range(B.N_BATCHES)]
@@ -187,5 +192,8 @@ def bench(args, rank, world, eng, barrier):
     return {"seconds": seconds, "e2e_seconds": e2e_seconds,
             "clocks": clocks.stop() if clocks else None, "launches": model.launches_per_step * K * world,
             "roofline": roofline,
-            "e2e_api": "openrec_b200.sharded.ShardedPairwise.step; pinned host ids in, global loss to host each step",
-            "extra": {"last_loss": [float(x) for x in last], "total_items": I, "total_users": U}}
+            "e2e_api": ("openrec_b200.sharded_peer.PeerShardedPairwise.step" if use_peer else
+                        "openrec_b200.sharded.ShardedPairwise.step") + "; pinned host ids in, global loss to host each step",
+            "extra": {"last_loss": [float(x) for x in last], "total_items": I, "total_users": U,
+                      "exchange": "NVLink peer loads/stores inside liborx kernels (CUDA IPC), 2 barriers/step" if use_peer
+                      else "NCCL all-to-all (counts, ids, rows, gradient rows)"}}

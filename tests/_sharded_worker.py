@@ -14,7 +14,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     out_path, kind, opt_kind = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    on_gpu = len(sys.argv) > 4 and sys.argv[4] == "gpu"
+    on_gpu = len(sys.argv) > 4 and sys.argv[4] in ("gpu", "peer")
+    peer = len(sys.argv) > 4 and sys.argv[4] == "peer"
     from openrec_b200.sharded import ShardedPairwise
     if on_gpu:   # the real kernels, one process per GPU over NCCL
         torch.cuda.set_device(rank)
@@ -30,7 +31,11 @@ def main():
     U, I, D, B = (61, 83, 16, 40) if not on_gpu else (1501, 2003, 128, 1024)
     sc = 0.05 if kind == 0 else 0.4
     user, item, bias = (rng.uniform(-sc, sc, s).astype(np.float32) for s in ((U, D), (I, D), (I, 1)))
-    m = ShardedPairwise(engine, rank, world, U, I, D, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
+    if peer:   # one-sided NVLink peer-memory step
+        from openrec_b200.sharded_peer import PeerShardedPairwise
+        m = PeerShardedPairwise(engine, rank, world, U, I, D, B, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
+    else:
+        m = ShardedPairwise(engine, rank, world, U, I, D, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
     m.load_global(user, item, bias)
     losses = []
     for step in range(3):
@@ -40,6 +45,8 @@ def main():
     full = [t.cpu().numpy() for t in m.gather_global()]
     if rank == 0:
         np.savez(out_path, user=full[0], item=full[1], bias=full[2], losses=np.stack(losses))
+    if peer:
+        m.close()
     dist.destroy_process_group()
 
 

@@ -14,8 +14,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("mode", ["gpu", "peer"])     # NCCL all-to-all path / one-sided NVLink peer-memory path
 @pytest.mark.parametrize("kind,opt_kind", [(0, 1), (0, 0), (1, 1)])
-def test_sharded_step_on_gpus(tmp_path, kind, opt_kind):
+def test_sharded_step_on_gpus(tmp_path, kind, opt_kind, mode):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
@@ -25,7 +26,7 @@ def test_sharded_step_on_gpus(tmp_path, kind, opt_kind):
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_sharded_worker.py"), out,
-                                       str(kind), str(opt_kind), "gpu"], env=env, stdout=subprocess.PIPE,
+                                       str(kind), str(opt_kind), mode], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
     for p in procs:
         o, _ = p.communicate(timeout=600)
