@@ -47,8 +47,8 @@ def workload_name(n_gpus):
     s = (f"BPR {U} users x {I} items, dim {D}, batch {B} per GPU, Adagrad lr {LR} (acc init 0.1), "
          f"ids uniform i.i.d. int32, {N_BATCHES} rotating id batches")
     if n_gpus > 1:
-        s += (f", 1M users + 12.5M items per GPU row-sharded over {n_gpus} GPUs (row r on rank r % N), rows gathered and "
-              "gradients pushed over NVLink peer memory")
+        s += (f", 1M users + 12.5M items per GPU row-sharded over {n_gpus} GPUs (row r on rank r % N), "
+              "NCCL all-to-all exchange of ids / rows / gradient rows")
     return s
 
 

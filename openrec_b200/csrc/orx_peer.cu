@@ -14,6 +14,8 @@
 //   k_inbox_index / k_inbox_apply / k_sparse_tail : each owner deduplicates ALL ranks' lookups of its rows (batch
 //                     hash), applies the optimizer once per unique row (rows hit once: straight from the inbox row).
 // Local layout per rank: combined table emb[user rows | item rows][D] + bias[user rows | item rows] (user part 0).
+#include <stdlib.h>
+
 #include "orx_common.cuh"
 
 struct PeerDev {
@@ -152,12 +154,16 @@ __global__ void __launch_bounds__(256) k_peer_step(PeerDev pd, const int32_t* __
     const float* rn = pd.emb[on] + ln * D;
     float4 uv[K], pv[K], nv[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {   // peer loads over NVLink (or local HBM when the owner is this rank)
-      uv[k] = *reinterpret_cast<const float4*>(ru + (k * 32 + lane) * 4);
-      pv[k] = *reinterpret_cast<const float4*>(rp + (k * 32 + lane) * 4);
-      nv[k] = *reinterpret_cast<const float4*>(rn + (k * 32 + lane) * 4);
+    // peer loads over NVLink (or local HBM when the owner is this rank); non-coherent path, the shards are read-only
+    // during the push.  NOTE (profiles/r1k_p2p_probe.txt): random 512 B rows from a peer mapping run at ~600 GB/s while
+    // the mapped shard is <= 2 GB but collapse to ~35 GB/s at 6.6 GB (translation reach of peer mappings); bulk peer
+    // copies are unaffected.  Large shards therefore want an owner-side gather into a compact outbox first.
+    for (int k = 0; k < K; ++k) {
+      uv[k] = __ldg(reinterpret_cast<const float4*>(ru + (k * 32 + lane) * 4));
+      pv[k] = __ldg(reinterpret_cast<const float4*>(rp + (k * 32 + lane) * 4));
+      nv[k] = __ldg(reinterpret_cast<const float4*>(rn + (k * 32 + lane) * 4));
     }
-    const float bp = pd.bias[op][lp], bn = pd.bias[on][ln];
+    const float bp = __ldg(pd.bias[op] + lp), bn = __ldg(pd.bias[on] + ln);
     float s1 = 0.f, s2 = 0.f, sq = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -275,15 +281,31 @@ extern "C" int orx_peer_pairwise_push(orx_handle_t h, int32_t kind, const void* 
   if (!h->bucket_cursor) ORX_CUDA(cudaMalloc(&h->bucket_cursor, sizeof(int32_t) * 1024));
   int32_t* counts = h->bucket_cursor + 512;
   int32_t* cursor = h->bucket_cursor;
+  static int dbg = -1;
+  static cudaEvent_t ev[6];
+  static int dbg_left = 0;
+  if (dbg < 0) {
+    dbg = getenv("ORX_PEER_DBG") ? 1 : 0;
+    if (dbg) {
+      for (int i = 0; i < 6; ++i) cudaEventCreate(&ev[i]);
+      dbg_left = 30;
+    }
+  }
+  const bool timing = dbg && dbg_left > 0;
+#define ORX_EV(i) do { if (timing) cudaEventRecord(ev[i], st); } while (0)
+  ORX_EV(0);
   ORX_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * R, st));
   int hb = (3 * B + 255) / 256;
   if (hb > h->num_sms * 4) hb = h->num_sms * 4;
   k_peer_hist<<<hb, 256, sizeof(int32_t) * R, st>>>(uid, pid, nid, B, R, counts);
   ORX_LAUNCH_CHECK();
+  ORX_EV(1);
   k_peer_publish<<<1, 64, 0, st>>>(counts, cursor, pd);
   ORX_LAUNCH_CHECK();
+  ORX_EV(2);
   k_peer_positions<<<(3 * B + 255) / 256, 256, 2 * sizeof(int32_t) * R, st>>>(uid, pid, nid, B, R, cursor, pos_scratch);
   ORX_LAUNCH_CHECK();
+  ORX_EV(3);
   const int blocks = h->num_sms * 8;
   int rc = orx_ensure_partials(h, blocks, st);
   if (rc) return rc;
@@ -292,7 +314,19 @@ extern "C" int orx_peer_pairwise_push(orx_handle_t h, int32_t kind, const void* 
   else { if (ph->dim == 128) ORX_PEER(ORX_PAIR_UCML, 1); else ORX_PEER(ORX_PAIR_UCML, 2); }
 #undef ORX_PEER
   ORX_LAUNCH_CHECK();
-  return orx_launch_reduce_partials(h->partials, blocks, kind == ORX_PAIR_BPR ? inv_B : 1.f, out4, st);
+  ORX_EV(4);
+  rc = orx_launch_reduce_partials(h->partials, blocks, kind == ORX_PAIR_BPR ? inv_B : 1.f, out4, st);
+  ORX_EV(5);
+  if (timing) {
+    cudaEventSynchronize(ev[5]);
+    float ms[5];
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    if (--dbg_left < 4 && ph->rank == 0)
+      fprintf(stderr, "[orx peer dbg] hist %.1f us | publish %.1f | positions %.1f | peer_step %.1f | reduce %.1f\n",
+              ms[0] * 1e3, ms[1] * 1e3, ms[2] * 1e3, ms[3] * 1e3, ms[4] * 1e3);
+  }
+#undef ORX_EV
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -129,8 +129,11 @@ def bench(args, rank, world, eng, barrier):
     K, W = args.steps, max(3, args.warmup)
     dev = eng.device
     U, I, D, Bsz = B.U, 12_500_000 * world, B.D, B.B      # BASELINE configs[4]: 100M items x 128 over 8 GPUs
-    use_peer = os.environ.get("ORX_SHARDED", "peer") != "nccl"
-    if use_peer:   # one-sided NVLink peer-memory step (sharded_peer.py); ORX_SHARDED=nccl selects the all-to-all path
+    # Default: NCCL all-to-all exchange.  ORX_SHARDED=peer selects the one-sided NVLink peer-memory step
+    # (sharded_peer.py) -- correct, and fast while a rank's shard stays below ~2 GB, but random 512 B rows from a
+    # 6.6 GB peer-mapped shard run at 35 GB/s (vs ~600 GB/s at 2 GB; profiles/r1k_p2p_probe.txt), so it is opt-in.
+    use_peer = os.environ.get("ORX_SHARDED", "nccl") == "peer"
+    if use_peer:
         from .sharded_peer import PeerShardedPairwise
         model = PeerShardedPairwise(eng, rank, world, U, I, D, Bsz, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
     else:

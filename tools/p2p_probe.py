@@ -9,7 +9,7 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 eng = N.engine(dev)
-rows, D = 4_000_000, 128                      # 2 GB
+rows, D = int(os.environ.get('P2P_ROWS', '4000000')), 128
 buf = _PeerBuf(eng, (rows, D), torch.float32)
 hs = [None] * world; dist.all_gather_object(hs, buf.handle)
 other = (rank + 1) % world
