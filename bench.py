@@ -189,7 +189,9 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's "NCCL version ..." banner goes to stdout; the contract is ONE JSON line
+        # NCCL prints its "NCCL version ..." banner to stdout whenever NCCL_DEBUG is set; the contract is ONE JSON line
+        os.environ.pop("NCCL_DEBUG", None)
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     eng = N.engine(dev)
 

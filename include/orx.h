@@ -250,6 +250,14 @@ ORX_API int orx_score_all(orx_handle_t h, int32_t kind, const float* user_tab, i
                   const float* scale, const float* item_tab, const float* item_bias, int64_t I, int32_t dim,
                   float* scores, orx_stream_t s);
 
+/* ---- device-side pairwise sampler (semantics of openrec/tf2/data/dataset.py:7-16 +
+ * data/utils.py:82-87,102-116): slot b takes record perm[(cursor+b) % n_records] and a uniform negative rejected while
+ * it is one of that user's positives (csr_off[U+1] / csr_items sorted per user). */
+ORX_API int orx_sample_pairwise(orx_handle_t h, const int32_t* rec_user, const int32_t* rec_item, const int64_t* perm,
+                                int64_t cursor, int64_t n_records, const int64_t* csr_off, const int32_t* csr_items,
+                                int32_t total_items, uint64_t seed, int32_t B, int32_t* uid, int32_t* pid, int32_t* nid,
+                                orx_stream_t s);
+
 /* ---- ranking metrics (openrec/tf2/metrics/ranking_metrics.py:8-69), one row per user --------
  * pos/excl are uint8 masks [R, I]; at[] (host) the cut-offs; outputs auc[R], ndcg[R,n_at], recall[R,n_at]
  * (any may be NULL). */

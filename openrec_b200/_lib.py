@@ -82,6 +82,7 @@ SIGNATURES = {
                            _vp, _vp, _vp, _vp, _vp, _vp],
     "orx_dense_apply": [_vp, _vp, _vp, _vp, _vp, _i64, _O, _vp],
     "orx_score_all": [_vp, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
+    "orx_sample_pairwise": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _u64, _i32, _vp, _vp, _vp, _vp],
     "orx_rank_metrics": [_vp, _vp, _vp, _vp, _i32, _i64, C.POINTER(_i32), _i32, _vp, _vp, _vp, _vp],
 }
 

@@ -3,3 +3,10 @@ from .utils import _DataStore, _ParallelDataset
 from .dataset import Dataset
 
 __all__ = ["Dataset", "_DataStore", "_ParallelDataset"]
+
+
+def __getattr__(name):   # lazy: keeps torch out of the spawned sampler workers
+    if name == "DevicePairwiseSampler":
+        from .device_sampler import DevicePairwiseSampler
+        return DevicePairwiseSampler
+    raise AttributeError(name)

@@ -214,3 +214,49 @@ def test_example_flow_end_to_end():
     assert len(lines) == 3, r.stdout
     aucs = [float(l.split("AUC:")[1].split(",")[0]) for l in lines]
     assert all(0.0 <= a <= 1.0 for a in aucs)
+
+
+def test_device_sampler_semantics(tf):
+    """DevicePairwiseSampler: every record exactly once per epoch, negatives never positive for the user."""
+    from openrec.tf2.data import Dataset, DevicePairwiseSampler
+    rng = np.random.default_rng(17)
+    U, I, n = 300, 500, 4000
+    pairs = np.unique(np.stack([rng.integers(0, U, n), rng.integers(0, I, n)], 1), axis=0)
+    raw = np.empty(len(pairs), dtype=[("user_id", np.int32), ("item_id", np.int32)])
+    raw["user_id"], raw["item_id"] = pairs[:, 0], pairs[:, 1]
+    ds = Dataset(raw_data=raw, total_users=U, total_items=I)
+    pos = set(map(tuple, pairs.tolist()))
+    B = 512
+    n_batches = len(raw) // B
+    it = DevicePairwiseSampler(ds, batch_size=B, take=2 * n_batches + 1, seed=3)
+    seen = []
+    for k, b in enumerate(it):
+        u, p, q = (b[x].numpy() for x in ("user_id", "p_item_id", "n_item_id"))
+        assert u.dtype == np.int32 and u.shape == (B,)
+        assert all((int(a), int(c)) in pos for a, c in zip(u, p))          # positives are records
+        assert not any((int(a), int(c)) in pos for a, c in zip(u, q))      # negatives are never positives
+        assert q.min() >= 0 and q.max() < I
+        if k < n_batches:
+            seen += list(zip(u.tolist(), p.tolist()))
+    assert k == 2 * n_batches and len(set(seen)) == len(seen) == n_batches * B   # no repeats inside an epoch
+
+
+def test_checkpoint_roundtrip(tf, tmp_path):
+    from openrec.tf2.recommenders import BPR
+    from openrec_b200.tf2 import checkpoint
+    rng = np.random.default_rng(18)
+    U, I, D, B = 100, 150, 64, 256
+    m1 = BPR(D, D, U, I)
+    o1 = tf.keras.optimizers.Adagrad(learning_rate=0.05)
+    ids = make_ids(rng, U, I, B)
+    train_step(tf, m1, o1, *ids)
+    checkpoint.save(tmp_path / "ck", m1, o1)
+    m2 = BPR(D, D, U, I)
+    o2 = tf.keras.optimizers.Adagrad(learning_rate=0.05)
+    checkpoint.load(tmp_path / "ck", m2, o2)
+    ids2 = make_ids(rng, U, I, B)
+    l1 = train_step(tf, m1, o1, *ids2)
+    l2 = train_step(tf, m2, o2, *ids2)
+    assert float(l1[0]) == float(l2[0])
+    for a, b in zip(snapshot(m1), snapshot(m2)):
+        assert np.array_equal(a, b)          # resumed run is bit-identical
