@@ -932,7 +932,7 @@ static bool pair_fused_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ORX_FUSED");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;   // opt-in: steady-state it is no faster than the 3-launch path (profiles/README.md r1g)
   }
   return v != 0;
 }
