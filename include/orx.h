@@ -209,6 +209,40 @@ ORX_API int orx_peer_apply(orx_handle_t h, const orx_table_t* emb, const orx_tab
                            const float* inbox_emb, const float* inbox_bias, const int32_t* inbox_cnt, int32_t world,
                            int64_t cap, const orx_opt_t* opt_host, orx_stream_t s);
 
+/* ---- mailbox exchange of the row-sharded step: peer STORES into small IPC-mapped mailboxes, no NCCL in the data
+ * path and no count on the host (openrec_b200/csrc/orx_xchg.cu, openrec_b200/sharded.py MailboxShardedPairwise).
+ * Replaces the four collectives of the NCCL form of SURVEY 8(e).  orx_xchg_t: DEVICE arrays of `world` peer pointers:
+ *   idbox int32[world][cap]   ids requested from me, per source rank      meta int32[world][4] per-peer counters
+ *   got   float[cap][width]   rows for my lookups, in my owner-sorted order
+ *   gin   float[gin_rows][width] gradient rows for rows I own              flags int32[world+1] barrier epochs + error
+ * Call order per step: orx_owner_bucket_combined, orx_xchg_push_ids, barrier, orx_xchg_gather_push, barrier,
+ * orx_xchg_grad_push, barrier, orx_sparse_apply_devn(req, my gin, *n_dev).  orx_xchg_barrier is one such barrier
+ * (epoch strictly increasing; a peer that never arrives within timeout_ms leaves flags[world] = 1 instead of a hang). */
+typedef struct {
+  int32_t world, rank, width, cap;
+  void *idbox, *meta, *got, *gin, *flags;
+} orx_xchg_t;
+ORX_API int orx_xchg_push_ids(orx_handle_t h, const void* xchg_host /* orx_xchg_t* */, const int32_t* counts,
+                              const int32_t* send_local, int32_t n, orx_stream_t s);
+ORX_API int orx_xchg_gather_push(orx_handle_t h, const void* xchg_host, const float* table, int64_t rows,
+                                 int32_t gin_rows, int32_t* req, int32_t* n_dev, int32_t* n_bad, orx_stream_t s);
+ORX_API int orx_xchg_grad_push(orx_handle_t h, int32_t kind, const void* xchg_host, const int32_t* counts,
+                               const int32_t* slot, int32_t B, int32_t dim, float margin, float c_loss, float c_l2,
+                               float inv_B, float* out4, orx_stream_t s);
+ORX_API int orx_xchg_barrier(orx_handle_t h, const void* xchg_host, int32_t epoch, int32_t timeout_ms, orx_stream_t s);
+/* The whole step in ONE call: 8 launches + 3 flag barriers, nothing returns to the host.  work: int32[world + 1 +
+ * ceil(3B/1024)*world]; slot: int32[3B]; req: int32[gin_rows]; gin_local: local address of this rank's own gin;
+ * barriers use epochs epoch_base+1..+3. */
+ORX_API int orx_xchg_step(orx_handle_t h, int32_t kind, const void* xchg_host, const orx_table_t* tab,
+                          const int32_t* uid, const int32_t* pid, const int32_t* nid, int32_t B, int64_t total_users,
+                          int32_t dim, const float* gin_local, int32_t gin_rows, int32_t* work, int32_t* slot,
+                          int32_t* req, float margin, float c_loss, float c_l2, float inv_B, const orx_opt_t* opt_host,
+                          int32_t epoch_base, int32_t timeout_ms, float* out4, orx_stream_t s);
+/* orx_sparse_apply with the pair count read from the device (*n_dev <= n_max); value rows have stride value_ld. */
+ORX_API int orx_sparse_apply_devn(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
+                                  int64_t value_ld, int32_t n_max, const int32_t* n_dev, const orx_opt_t* opt_host,
+                                  orx_stream_t s);
+
 /* ---- dense variables (GMF w, MLP kernels/biases): Keras dense apply ---------------------- */
 ORX_API int orx_dense_apply(orx_handle_t h, float* var, float* s0, float* s1, const float* grad, int64_t n,
                     const orx_opt_t* opt_host, orx_stream_t s);

@@ -35,6 +35,12 @@ class OrxPeer(C.Structure):
                 ("inbox_ids", C.c_void_p), ("inbox_cnt", C.c_void_p)]
 
 
+class OrxXchg(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("width", C.c_int32), ("cap", C.c_int32),
+                ("idbox", C.c_void_p), ("meta", C.c_void_p), ("got", C.c_void_p), ("gin", C.c_void_p),
+                ("flags", C.c_void_p)]
+
+
 _vp, _i32, _i64, _f, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 _T = C.POINTER(OrxTable)
 _O = C.POINTER(OrxOpt)
@@ -73,6 +79,13 @@ SIGNATURES = {
     "orx_peer_free": [_vp, _vp],
     "orx_peer_pairwise_push": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _f, _f, _f, _f, _vp, _vp],
     "orx_peer_apply": [_vp, _T, _T, _vp, _vp, _vp, _vp, _i32, _i64, _O, _vp],
+    "orx_xchg_push_ids": [_vp, _vp, _vp, _vp, _i32, _vp],
+    "orx_xchg_gather_push": [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp],
+    "orx_xchg_grad_push": [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _f, _f, _f, _f, _vp, _vp],
+    "orx_xchg_barrier": [_vp, _vp, _i32, _i32, _vp],
+    "orx_xchg_step": [_vp, _i32, _vp, _T, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _f, _f, _f, _f, _O,
+                      _i32, _i32, _vp, _vp],
+    "orx_sparse_apply_devn": [_vp, _T, _vp, _vp, _i64, _i32, _vp, _O, _vp],
     "orx_owner_bucket_combined": [_vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
     "orx_pairwise_grad_rows": [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _f, _f, _f, _f, _vp, _vp, _vp],
     "orx_owner_bucket": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],

@@ -250,7 +250,7 @@ struct TailArgs {
 
 OrxOptDev orx_opt_to_dev(const orx_opt_t* o);
 int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride, int64_t rows, int32_t n,
-                                   bool stage_all, cudaStream_t st);
+                                   const int32_t* n_dev, bool stage_all, cudaStream_t st);
 int orx_launch_tail(orx_ctx* c, const TailArgs& ta, int opt_kind, cudaStream_t st);
 struct PairArgs;
 int orx_launch_pair_fused(orx_ctx* c, int kind, int opt_kind, PairArgs& pa, float loss_scale, float* out4,

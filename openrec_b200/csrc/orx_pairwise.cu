@@ -40,20 +40,22 @@ __global__ void k_index_build(OrxHash hu, OrxHash hi, const int32_t* __restrict_
 }
 
 __global__ void k_index_build_strided(OrxHash hu, const int32_t* __restrict__ a, int64_t stride, int64_t rows, int n,
-                                       int stage_all, int32_t* bad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int32_t id = a[(int64_t)i * stride];
-  if (id >= 0 && (int64_t)id < rows) orx_hash_insert(hu, id, stage_all);
-  else atomicAdd(bad, 1);
+                                       const int32_t* __restrict__ n_dev, int stage_all, int32_t* bad) {
+  if (n_dev) n = min(n, *n_dev);   // count produced on the device (mailbox exchange): grid-stride over it
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int32_t id = a[(int64_t)i * stride];
+    if (id >= 0 && (int64_t)id < rows) orx_hash_insert(hu, id, stage_all);
+    else atomicAdd(bad, 1);
+  }
 }
 
 int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride, int64_t rows, int32_t n,
-                                   bool stage_all, cudaStream_t st) {
+                                   const int32_t* n_dev, bool stage_all, cudaStream_t st) {
   if (n <= 0) return ORX_OK;
   orx_new_epoch(c);
-  k_index_build_strided<<<(n + 255) / 256, 256, 0, st>>>(c->hu, a, stride, rows, n, stage_all ? 1 : 0,
-                                                         c->counters + 3);
+  int blocks = (n + 255) / 256;
+  if (n_dev && blocks > c->num_sms * 8) blocks = c->num_sms * 8;
+  k_index_build_strided<<<blocks, 256, 0, st>>>(c->hu, a, stride, rows, n, n_dev, stage_all ? 1 : 0, c->counters + 3);
   ORX_LAUNCH_CHECK();
   return ORX_OK;
 }

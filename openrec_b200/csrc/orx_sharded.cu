@@ -116,20 +116,32 @@ template <int OPT>
 __global__ void __launch_bounds__(256) k_sparse_apply(float* var, float* s0, float* s1, int64_t rows, int D,
                                                       const int32_t* __restrict__ ids, int64_t id_stride,
                                                       const float* __restrict__ vals, int64_t val_ld, int n,
-                                                      OrxHash hsh, float* gstage, OrxOptDev o) {
+                                                      const int32_t* __restrict__ n_dev, OrxHash hsh, float* gstage,
+                                                      OrxOptDev o) {
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool STAGE_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
   const int lane = threadIdx.x & 31;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= n) return;
-  const int32_t id = ids[(int64_t)b * id_stride];
-  if (id < 0 || (int64_t)id >= rows) return;
-  int d = -1;
-  uint32_t c = 0;
-  if (lane == 0) c = orx_hash_find(hsh, id, &d);
-  c = __shfl_sync(ORX_FULL, c, 0);
-  d = __shfl_sync(ORX_FULL, d, 0);
+  if (n_dev) n = min(n, *n_dev);   // count produced on the device: the grid is capped and strides over it
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  // a warp takes 8 consecutive pairs per iteration; lanes 0..7 load the ids and probe the hash in parallel
+  for (int b0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8; b0 < n; b0 += nw * 8) {
+  int32_t my_id = -1;
+  int my_d = -1;
+  uint32_t my_c = 0;
+  if (lane < 8 && b0 + lane < n) {
+    my_id = ids[(int64_t)(b0 + lane) * id_stride];
+    if (my_id < 0 || (int64_t)my_id >= rows) my_id = -1;
+    else my_c = orx_hash_find(hsh, my_id, &my_d);
+  }
+#pragma unroll 2
+  for (int k = 0; k < 8; ++k) {
+  const int b = b0 + k;
+  if (b >= n) break;
+  const int32_t id = __shfl_sync(ORX_FULL, my_id, k);
+  const uint32_t c = __shfl_sync(ORX_FULL, my_c, k);
+  const int d = __shfl_sync(ORX_FULL, my_d, k);
+  if (id < 0) continue;
   const float* v = vals + (int64_t)b * val_ld;
   const bool vec = ((D & 3) == 0) && ((val_ld & 3) == 0);
   if (!STAGE_ONLY && c == 1u) {
@@ -160,6 +172,8 @@ __global__ void __launch_bounds__(256) k_sparse_apply(float* var, float* s0, flo
   } else {
     for (int e = lane; e < D; e += 32) atomicAdd(gstage + (int64_t)d * D + e, v[e]);
   }
+  }
+  }
 }
 
 // tail for one table: staged rows -> optimizer, staging zeroed, hash cleared, counters reset
@@ -174,6 +188,23 @@ __global__ void __launch_bounds__(256) k_sparse_apply_tail(float* var, float* s0
   const int ns = *hsh.counter;
   for (int r = gwarp; r < ns; r += nwarps) {
     const int id = hsh.did[r];
+    if ((D & 3) == 0) {   // 128-bit path
+      for (int e = lane * 4; e < D; e += 128) {
+        const int64_t off = (int64_t)id * D + e;
+        float4* gp = reinterpret_cast<float4*>(gstage + (int64_t)r * D + e);
+        if (!ZERO_ONLY) {
+          const float4 g = __ldcg(gp);
+          float4 wv = __ldcg(reinterpret_cast<const float4*>(var + off));
+          float4 a = S0 ? __ldcg(reinterpret_cast<const float4*>(s0 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 bb = S1 ? __ldcg(reinterpret_cast<const float4*>(s1 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          __stcg(reinterpret_cast<float4*>(var + off), orx_apply4<OPT>(wv, g, a, bb, o));
+          if (S0) __stcg(reinterpret_cast<float4*>(s0 + off), a);
+          if (S1) __stcg(reinterpret_cast<float4*>(s1 + off), bb);
+        }
+        __stcg(gp, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+      continue;
+    }
     for (int e = lane; e < D; e += 32) {
       const int64_t off = (int64_t)id * D + e;
       if (!ZERO_ONLY) {
@@ -196,23 +227,34 @@ __global__ void __launch_bounds__(256) k_sparse_apply_tail(float* var, float* s0
 }
 
 static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
-                             const float* values, int64_t value_ld, int32_t n, const orx_opt_t* opt, orx_stream_t s);
+                             const float* values, int64_t value_ld, int32_t n, const int32_t* n_dev,
+                             const orx_opt_t* opt, orx_stream_t s);
 
 extern "C" int orx_sparse_apply(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
                                 int32_t n, const orx_opt_t* opt, orx_stream_t s) {
   ORX_REQUIRE(tab != nullptr, "null table");
-  return sparse_apply_impl(h, tab, ids, 1, values, tab->dim, n, opt, s);
+  return sparse_apply_impl(h, tab, ids, 1, values, tab->dim, n, nullptr, opt, s);
 }
 
 extern "C" int orx_sparse_apply_strided(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
                                         const float* values, int64_t value_ld, int32_t n, const orx_opt_t* opt,
                                         orx_stream_t s) {
   ORX_REQUIRE(tab != nullptr && id_stride >= 1 && value_ld >= tab->dim, "bad strides");
-  return sparse_apply_impl(h, tab, ids, id_stride, values, value_ld, n, opt, s);
+  return sparse_apply_impl(h, tab, ids, id_stride, values, value_ld, n, nullptr, opt, s);
+}
+
+// Same, but the number of (id, value-row) pairs is only known on the device (*n_dev <= n_max): the mailbox exchange's
+// owner side (orx_xchg.cu), where the count is the sum of what the peers pushed.  No host round trip.
+extern "C" int orx_sparse_apply_devn(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
+                                     int64_t value_ld, int32_t n_max, const int32_t* n_dev, const orx_opt_t* opt,
+                                     orx_stream_t s) {
+  ORX_REQUIRE(tab != nullptr && n_dev != nullptr && value_ld >= tab->dim && n_max > 0, "bad arguments");
+  return sparse_apply_impl(h, tab, ids, 1, values, value_ld, n_max, n_dev, opt, s);
 }
 
 static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
-                             const float* values, int64_t value_ld, int32_t n, const orx_opt_t* opt, orx_stream_t s) {
+                             const float* values, int64_t value_ld, int32_t n, const int32_t* n_dev,
+                             const orx_opt_t* opt, orx_stream_t s) {
   ORX_REQUIRE(h != nullptr && tab && tab->var && opt, "null pointer");
   ORX_REQUIRE(n >= 0 && tab->rows > 0 && tab->dim > 0, "bad sizes");
   ORX_REQUIRE(opt->kind >= ORX_OPT_SGD && opt->kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
@@ -229,13 +271,14 @@ static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32
   const OrxOptDev o = orx_opt_to_dev(opt);
   // the user-side hash / staging pair serves as "the" table here
   if (n > 0) {
-    if ((rc = orx_launch_index_build_strided(h, ids, id_stride, tab->rows, n, dense, st))) return rc;
-    const int blocks = (n + 7) / 8;
+    if ((rc = orx_launch_index_build_strided(h, ids, id_stride, tab->rows, n, n_dev, dense, st))) return rc;
+    int blocks = (n + 63) / 64;   // 8 warps x 8 pairs per block and iteration
+    if (n_dev && blocks > h->num_sms * 8) blocks = h->num_sms * 8;
     switch (opt->kind) {
-      case ORX_OPT_SGD: k_sparse_apply<ORX_OPT_SGD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, h->hu, h->gu, o); break;
-      case ORX_OPT_ADAGRAD: k_sparse_apply<ORX_OPT_ADAGRAD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, h->hu, h->gu, o); break;
-      case ORX_OPT_ADAM_LAZY: k_sparse_apply<ORX_OPT_ADAM_LAZY><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, h->hu, h->gu, o); break;
-      default: k_sparse_apply<ORX_OPT_ADAM_DENSE><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, h->hu, h->gu, o); break;
+      case ORX_OPT_SGD: k_sparse_apply<ORX_OPT_SGD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, n_dev, h->hu, h->gu, o); break;
+      case ORX_OPT_ADAGRAD: k_sparse_apply<ORX_OPT_ADAGRAD><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, n_dev, h->hu, h->gu, o); break;
+      case ORX_OPT_ADAM_LAZY: k_sparse_apply<ORX_OPT_ADAM_LAZY><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, n_dev, h->hu, h->gu, o); break;
+      default: k_sparse_apply<ORX_OPT_ADAM_DENSE><<<blocks, 256, 0, st>>>(tab->var, tab->s0, tab->s1, tab->rows, D, ids, id_stride, values, value_ld, n, n_dev, h->hu, h->gu, o); break;
     }
     ORX_LAUNCH_CHECK();
   }

@@ -120,6 +120,138 @@ class ShardedPairwise:
         return outs
 
 
+class MailboxShardedPairwise(ShardedPairwise):
+    """Same partitioning and arithmetic as ShardedPairwise, but the three exchanges are liborx kernels that STORE into
+    the peers' mailboxes over NVLink (CUDA IPC mappings; csrc/orx_xchg.cu) -- no NCCL in the data path, no host sync.
+    ``torch.distributed`` is used once to swap the IPC handles, and (``barrier="nccl"``) for the three tiny
+    stream-ordered barriers of a step; ``barrier="flag"`` uses orx_xchg_barrier (flags in peer memory) instead.
+
+    Buffer reuse across steps is ordered by the same barriers: idbox is rewritten after C(t) and read before B(t);
+    got is rewritten after A(t+1) and read before C(t); gin is rewritten after B(t+1) and read by the owner's apply
+    of step t, which precedes its arrival at A(t+1)."""
+
+    def __init__(self, eng, rank, world, total_users, total_items, dim, batch, *, barrier=None, gin_rows=None, **kw):
+        super().__init__(eng, rank, world, total_users, total_items, dim, **kw)
+        import ctypes as C
+
+        import numpy as np
+
+        from .sharded_peer import _PeerBuf
+        if dim % 4:
+            raise ValueError("the mailbox exchange needs dim % 4 == 0")
+        self.B = batch
+        self.cap = 3 * batch
+        self.gin_rows = int(gin_rows or world * self.cap)        # worst case: every rank's lookups land on me
+        self.barrier_kind = barrier or os.environ.get("ORX_XCHG_BARRIER", "flag")
+        dev = eng.device
+        W = self.W
+        self._bufs = [_PeerBuf(eng, (world * self.cap,), torch.int32),      # idbox
+                      _PeerBuf(eng, (world * 4,), torch.int32),             # meta
+                      _PeerBuf(eng, (self.cap, W), torch.float32),          # got
+                      _PeerBuf(eng, (self.gin_rows, W), torch.float32),     # gin
+                      _PeerBuf(eng, (world + 1,), torch.int32)]             # flags
+        for b in self._bufs:
+            b.t.zero_()
+        torch.cuda.synchronize()
+        everyone = [None] * world
+        dist.all_gather_object(everyone, [b.handle for b in self._bufs])
+        self._opened = []
+        ptrs = np.zeros((5, world), dtype=np.int64)
+        for r in range(world):
+            for k in range(5):
+                if r == rank:
+                    ptrs[k, r] = self._bufs[k].ptr
+                else:
+                    p = C.c_void_p()
+                    _lib.check(eng.lib.orx_peer_open(eng.h, everyone[r][k], C.byref(p)), "orx_peer_open")
+                    self._opened.append(p.value)
+                    ptrs[k, r] = p.value
+        self._ptrs = torch.from_numpy(ptrs).to(dev)
+        base = self._ptrs.data_ptr()
+        self._x = _lib.OrxXchg(world, rank, W, self.cap, *[base + 8 * world * k for k in range(5)])
+        self._req = torch.empty(self.gin_rows, dtype=torch.int32, device=dev)
+        self._n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._epoch = 0
+        self._work = torch.zeros(world + 1 + ((self.cap + 1023) // 1024) * world, dtype=torch.int32, device=dev)
+        self._slot = torch.empty(self.cap, dtype=torch.int32, device=dev)
+        self._out = torch.zeros(16, 4, dtype=torch.float32, device=dev)     # ring of step outputs (loss, l2, -, -)
+        self.fused_call = os.environ.get("ORX_XCHG_FUSED", "1") != "0" and self.barrier_kind == "flag"
+        self.launches_per_step = 2 + 1 + 2 + 3 + 3   # hist, scatter+push, gather+push, grads+reduce, apply(3), 3 barriers
+        dist.barrier()
+
+    def _barrier(self):
+        import ctypes as C
+        if self.barrier_kind == "flag":
+            self._epoch += 1
+            _lib.check(self.eng.lib.orx_xchg_barrier(self.eng.h, C.byref(self._x), self._epoch, 5000, self.eng.stream()),
+                       "orx_xchg_barrier")
+        else:
+            dist.all_reduce(self._flag)
+
+    def step(self, uid, pid, nid, c_loss=1.0, c_l2=1.0, reduce_loss=True):
+        import ctypes as C
+        eng, R, D, W = self.eng, self.world, self.D, self.W
+        B = uid.numel()
+        if B > self.B:
+            raise ValueError("batch larger than the mailboxes this model was built for")
+        self.iterations += 1
+        x, st = C.byref(self._x), eng.stream()
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        if self.fused_call:       # one C call: bucket + push, gather + push, grads + push, apply, 3 flag barriers
+            out4 = self._out[self.iterations % 16]
+            o = eng.make_opt(self.opt_kind, self.lr, self.eps, self.b1, self.b2, self.iterations)
+            tab = eng.make_table(self.table, *self.slots)
+            _lib.check(eng.lib.orx_xchg_step(eng.h, self.kind, x, C.byref(tab), vp(uid), vp(pid), vp(nid), B, self.U, D,
+                                             C.c_void_p(self._bufs[3].ptr), self.gin_rows, vp(self._work),
+                                             vp(self._slot), vp(self._req), self.margin, c_loss, c_l2, 1.0 / (B * R),
+                                             C.byref(o), self._epoch, 5000, vp(out4), st), "orx_xchg_step")
+            self._epoch += 3
+            out = out4[:2]
+            if reduce_loss:
+                out = out.clone()
+                dist.all_reduce(out)
+            return out
+        ids = torch.cat([uid, pid, nid])
+        counts, send_local, slot = eng.owner_bucket_combined(ids, B, self.U, R)
+        _lib.check(eng.lib.orx_xchg_push_ids(eng.h, x, vp(counts), vp(send_local), 3 * B, st), "orx_xchg_push_ids")
+        self._barrier()                                                # A: every owner has its requests
+        _lib.check(eng.lib.orx_xchg_gather_push(eng.h, x, vp(self.table), self.table.shape[0], self.gin_rows,
+                                                vp(self._req), vp(self._n_dev), None, st), "orx_xchg_gather_push")
+        self._barrier()                                                # B: my rows (and inbox bases) have landed
+        out4 = torch.zeros(4, dtype=torch.float32, device=uid.device)
+        _lib.check(eng.lib.orx_xchg_grad_push(eng.h, self.kind, x, vp(counts), vp(slot), B, D, self.margin, c_loss, c_l2,
+                                              1.0 / (B * R), vp(out4), st), "orx_xchg_grad_push")
+        self._barrier()                                                # C: every gradient row is in its owner's inbox
+        o = eng.make_opt(self.opt_kind, self.lr, self.eps, self.b1, self.b2, self.iterations)
+        tab = eng.make_table(self.table, *self.slots)
+        _lib.check(eng.lib.orx_sparse_apply_devn(eng.h, C.byref(tab), vp(self._req), C.c_void_p(self._bufs[3].ptr), W,
+                                                 self.gin_rows, vp(self._n_dev), C.byref(o), st),
+                   "orx_sparse_apply_devn")
+        out = out4[:2].clone()
+        if reduce_loss:
+            dist.all_reduce(out)
+        return out
+
+    def check(self):
+        """Raise if a barrier timed out or a gradient inbox overflowed (sticky device flag; one tiny D2H read)."""
+        code = int(self._bufs[4].t[self.world].item())
+        if code:
+            raise RuntimeError({1: "mailbox barrier timed out: a peer rank never arrived",
+                                2: "gradient inbox overflow: rebuild with a larger gin_rows"}.get(code, f"error {code}"))
+
+    def close(self):
+        import ctypes as C
+        torch.cuda.synchronize()
+        dist.barrier()
+        for p in self._opened:
+            self.eng.lib.orx_peer_close(self.eng.h, C.c_void_p(p))
+        self._opened = []
+        dist.barrier()
+        for b in self._bufs:
+            b.free()
+
+
 # ---------------------------------------------------------------------------------------
 # bench.py's N>1 leg
 # ---------------------------------------------------------------------------------------
@@ -132,8 +264,11 @@ def bench(args, rank, world, eng, barrier):
     # Default: NCCL all-to-all exchange.  ORX_SHARDED=peer selects the one-sided NVLink peer-memory step
     # (sharded_peer.py) -- correct, and fast while a rank's shard stays below ~2 GB, but random 512 B rows from a
     # 6.6 GB peer-mapped shard run at 35 GB/s (vs ~600 GB/s at 2 GB; profiles/r1k_p2p_probe.txt), so it is opt-in.
-    use_peer = os.environ.get("ORX_SHARDED", "nccl") == "peer"
-    if use_peer:
+    mode = os.environ.get("ORX_SHARDED", "mailbox")
+    use_peer = mode == "peer"
+    if mode == "mailbox":
+        model = MailboxShardedPairwise(eng, rank, world, U, I, D, Bsz, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
+    elif use_peer:
         from .sharded_peer import PeerShardedPairwise
         model = PeerShardedPairwise(eng, rank, world, U, I, D, Bsz, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
     else:
@@ -183,6 +318,8 @@ def bench(args, rank, world, eng, barrier):
     if clocks:
         clocks.window(t0, t1)
     e2e_seconds = e0.elapsed_time(e1) * 1e-3
+    if hasattr(model, "check"):
+        model.check()
     # NVLink-bound exchange: bytes per GPU per direction per step
     link_bytes = 2.0 * (world - 1) / world * (3 * D + 2) * 4 * Bsz
     nvlink_peak = 770.0
@@ -195,8 +332,10 @@ def bench(args, rank, world, eng, barrier):
     return {"seconds": seconds, "e2e_seconds": e2e_seconds,
             "clocks": clocks.stop() if clocks else None, "launches": model.launches_per_step * K * world,
             "roofline": roofline,
-            "e2e_api": ("openrec_b200.sharded_peer.PeerShardedPairwise.step" if use_peer else
-                        "openrec_b200.sharded.ShardedPairwise.step") + "; pinned host ids in, global loss to host each step",
+            "e2e_api": f"openrec_b200.{type(model).__module__.split('.')[-1]}.{type(model).__name__}.step"
+                       "; pinned host ids in, global loss to host each step",
             "extra": {"last_loss": [float(x) for x in last], "total_items": I, "total_users": U,
-                      "exchange": "NVLink peer loads/stores inside liborx kernels (CUDA IPC), 2 barriers/step" if use_peer
-                      else "NCCL all-to-all (counts, ids, rows, gradient rows)"}}
+                      "exchange": {"peer": "NVLink peer loads/stores inside liborx kernels (CUDA IPC), 2 barriers/step",
+                                   "mailbox": "liborx kernels storing ids / rows / gradient rows into the peers' IPC-mapped "
+                                              "mailboxes over NVLink, 3 device-side flag barriers, no host sync",
+                                   }.get(mode, "NCCL all-to-all (counts, ids, rows, gradient rows)")}}

@@ -14,9 +14,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     out_path, kind, opt_kind = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    on_gpu = len(sys.argv) > 4 and sys.argv[4] in ("gpu", "peer")
-    peer = len(sys.argv) > 4 and sys.argv[4] == "peer"
-    from openrec_b200.sharded import ShardedPairwise
+    mode = sys.argv[4] if len(sys.argv) > 4 else "cpu"
+    on_gpu = mode != "cpu"
+    peer = mode == "peer"
+    from openrec_b200.sharded import MailboxShardedPairwise, ShardedPairwise
     if on_gpu:   # the real kernels, one process per GPU over NCCL
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -34,6 +35,9 @@ def main():
     if peer:   # one-sided NVLink peer-memory step
         from openrec_b200.sharded_peer import PeerShardedPairwise
         m = PeerShardedPairwise(engine, rank, world, U, I, D, B, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
+    elif mode.startswith("mailbox"):   # peer-store mailboxes; "mailbox-nccl": NCCL all-reduce as the barrier
+        m = MailboxShardedPairwise(engine, rank, world, U, I, D, B, kind=kind, opt_kind=opt_kind, lr=0.05, init=False,
+                                   barrier="nccl" if mode.endswith("nccl") else "flag")
     else:
         m = ShardedPairwise(engine, rank, world, U, I, D, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
     m.load_global(user, item, bias)
@@ -45,7 +49,9 @@ def main():
     full = [t.cpu().numpy() for t in m.gather_global()]
     if rank == 0:
         np.savez(out_path, user=full[0], item=full[1], bias=full[2], losses=np.stack(losses))
-    if peer:
+    if hasattr(m, "check"):
+        m.check()
+    if hasattr(m, "close"):
         m.close()
     dist.destroy_process_group()
 

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("mode", ["gpu", "peer"])     # NCCL all-to-all path / one-sided NVLink peer-memory path
+# NCCL all-to-all path / peer-store mailboxes (flag barrier, NCCL barrier) / one-sided peer-load path
+@pytest.mark.parametrize("mode", ["gpu", "mailbox", "mailbox-nccl", "peer"])
 @pytest.mark.parametrize("kind,opt_kind", [(0, 1), (0, 0), (1, 1)])
 def test_sharded_step_on_gpus(tmp_path, kind, opt_kind, mode):
     world = min(torch.cuda.device_count(), 4)
