@@ -212,7 +212,7 @@ ORX_API int orx_peer_apply(orx_handle_t h, const orx_table_t* emb, const orx_tab
 /* ---- mailbox exchange of the row-sharded step: peer STORES into small IPC-mapped mailboxes, no NCCL in the data
  * path and no count on the host (openrec_b200/csrc/orx_xchg.cu, openrec_b200/sharded.py MailboxShardedPairwise).
  * Replaces the four collectives of the NCCL form of SURVEY 8(e).  orx_xchg_t: DEVICE arrays of `world` peer pointers:
- *   idbox int32[world][cap]   ids requested from me, per source rank      meta int32[world][4] per-peer counters
+ *   idbox int32[world][cap]   ids requested from me, per source rank      meta int32[world][8] per-peer counters + loss
  *   got   float[cap][width]   rows for my lookups, in my owner-sorted order
  *   gin   float[gin_rows][width] gradient rows for rows I own              flags int32[world+1] barrier epochs + error
  * Call order per step: orx_owner_bucket_combined, orx_xchg_push_ids, barrier, orx_xchg_gather_push, barrier,
@@ -230,7 +230,8 @@ ORX_API int orx_xchg_grad_push(orx_handle_t h, int32_t kind, const void* xchg_ho
                                const int32_t* slot, int32_t B, int32_t dim, float margin, float c_loss, float c_l2,
                                float inv_B, float* out4, orx_stream_t s);
 ORX_API int orx_xchg_barrier(orx_handle_t h, const void* xchg_host, int32_t epoch, int32_t timeout_ms, orx_stream_t s);
-/* The whole step in ONE call: 8 launches + 3 flag barriers, nothing returns to the host.  work: int32[world + 1 +
+/* The whole step in ONE call: 9 launches + 3 flag barriers, nothing returns to the host; out4[0..1] is the GLOBAL
+ * (loss, l2_loss) on every rank (partials ride the meta mailboxes, no collective).  work: int32[world + 1 +
  * ceil(3B/1024)*world]; slot: int32[3B]; req: int32[gin_rows]; gin_local: local address of this rank's own gin;
  * barriers use epochs epoch_base+1..+3. */
 ORX_API int orx_xchg_step(orx_handle_t h, int32_t kind, const void* xchg_host, const orx_table_t* tab,

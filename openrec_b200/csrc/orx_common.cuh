@@ -66,6 +66,8 @@ struct orx_ctx {
   int prof_on, prof_n, prof_cap;
   cudaEvent_t* prof_ev;  // [prof_cap*4]
   int32_t* bucket_cursor;  // owner-bucket scratch
+  cudaStream_t side_stream;  // orx_xchg_step: index build overlapped with the gradient exchange
+  cudaEvent_t side_ev[2];
   uint32_t epoch;          // hash epoch of the last step
 };
 
@@ -249,6 +251,8 @@ struct TailArgs {
 };
 
 OrxOptDev orx_opt_to_dev(const orx_opt_t* o);
+int orx_sparse_apply_prebuilt(orx_ctx* h, const orx_table_t* tab, const int32_t* ids, const float* values, int64_t value_ld,
+                              int32_t n_max, const int32_t* n_dev, const orx_opt_t* opt, cudaStream_t st);
 int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride, int64_t rows, int32_t n,
                                    const int32_t* n_dev, bool stage_all, cudaStream_t st);
 int orx_launch_tail(orx_ctx* c, const TailArgs& ta, int opt_kind, cudaStream_t st);

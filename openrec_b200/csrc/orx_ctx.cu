@@ -151,6 +151,11 @@ extern "C" int orx_destroy(orx_handle_t h) {
   cudaFree(h->counters);
   cudaFree(h->partials);
   cudaFree(h->bucket_cursor);
+  if (h->side_stream) {
+    cudaStreamDestroy(h->side_stream);
+    cudaEventDestroy(h->side_ev[0]);
+    cudaEventDestroy(h->side_ev[1]);
+  }
   if (h->prof_ev) {
     for (int i = 0; i < h->prof_cap * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) k_sparse_apply_tail(float* var, float* s0
 
 static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
                              const float* values, int64_t value_ld, int32_t n, const int32_t* n_dev,
-                             const orx_opt_t* opt, orx_stream_t s);
+                             const orx_opt_t* opt, orx_stream_t s, bool index_prebuilt = false);
 
 extern "C" int orx_sparse_apply(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
                                 int32_t n, const orx_opt_t* opt, orx_stream_t s) {
@@ -252,9 +252,17 @@ extern "C" int orx_sparse_apply_devn(orx_handle_t h, const orx_table_t* tab, con
   return sparse_apply_impl(h, tab, ids, 1, values, value_ld, n_max, n_dev, opt, s);
 }
 
+// orx_xchg_step builds the index of the owner's ids on a side stream while the gradient rows are still in flight,
+// then calls this with index_prebuilt = true (same workspace, same epoch).
+int orx_sparse_apply_prebuilt(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
+                              int64_t value_ld, int32_t n_max, const int32_t* n_dev, const orx_opt_t* opt,
+                              cudaStream_t st) {
+  return sparse_apply_impl(h, tab, ids, 1, values, value_ld, n_max, n_dev, opt, (orx_stream_t)st, true);
+}
+
 static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
                              const float* values, int64_t value_ld, int32_t n, const int32_t* n_dev,
-                             const orx_opt_t* opt, orx_stream_t s) {
+                             const orx_opt_t* opt, orx_stream_t s, bool index_prebuilt) {
   ORX_REQUIRE(h != nullptr && tab && tab->var && opt, "null pointer");
   ORX_REQUIRE(n >= 0 && tab->rows > 0 && tab->dim > 0, "bad sizes");
   ORX_REQUIRE(opt->kind >= ORX_OPT_SGD && opt->kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
@@ -271,7 +279,8 @@ static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32
   const OrxOptDev o = orx_opt_to_dev(opt);
   // the user-side hash / staging pair serves as "the" table here
   if (n > 0) {
-    if ((rc = orx_launch_index_build_strided(h, ids, id_stride, tab->rows, n, n_dev, dense, st))) return rc;
+    if (!index_prebuilt)
+      if ((rc = orx_launch_index_build_strided(h, ids, id_stride, tab->rows, n, n_dev, dense, st))) return rc;
     int blocks = (n + 63) / 64;   // 8 warps x 8 pairs per block and iteration
     if (n_dev && blocks > h->num_sms * 8) blocks = h->num_sms * 8;
     switch (opt->kind) {

@@ -28,7 +28,7 @@
 struct XchgDev {
   int world, rank, W, cap;        // cap: idbox entries per source rank (>= 3B)
   int32_t* const* idbox;          // [world] owner's int32 idbox[world][cap]
-  int32_t* const* meta;           // [world] peer's  int32 meta[world][4]: {count, sender's bucket offset, base in my gin, -}
+  int32_t* const* meta;           // [world] peer's  int32 meta[world][8]: {count, sender's bucket offset, base in my gin, -, loss, l2 (float bits), -, -}
   float* const* got;              // [world] requester's float got[cap][W]
   float* const* gin;              // [world] owner's float gin[gin_rows][W]
   int32_t* const* flags;          // [world] peer's int32 flags[world + 1]  (last entry: sticky error)
@@ -51,6 +51,7 @@ static XchgDev to_dev(const XchgHost* x) {
 }
 
 #define XCHG_MAX_R 64
+#define XCHG_META 8   // int32 words per peer in a meta mailbox
 
 // first r with off[r+1] > p   (off[0] = 0 <= p < off[R])
 __device__ __forceinline__ int xchg_bucket_of(const int32_t* off, int R, int p) {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(256) k_xchg_push_ids(XchgDev x, const int32_t*
   __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x < x.world) {
     const int o = threadIdx.x;
-    int32_t* m = x.meta[o] + 4 * x.rank;
+    int32_t* m = x.meta[o] + XCHG_META * x.rank;
     m[0] = counts[o];
     m[1] = off[o];
   }
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256) k_xchg_scatter_push(XchgDev x, const int3
   if (blockIdx.x == 0 && threadIdx.x < R) {
     const int o = threadIdx.x;
     counts_out[o] = tot[o];
-    int32_t* m = x.meta[o] + 4 * x.rank;
+    int32_t* m = x.meta[o] + XCHG_META * x.rank;
     m[0] = tot[o];
     m[1] = off[o];
   }
@@ -172,10 +173,10 @@ __global__ void __launch_bounds__(256) k_xchg_gather_push(XchgDev x, const float
     const int32_t* m = x.meta[me];
     int acc = 0;
     for (int s = 0; s < R; ++s) {
-      int c = m[4 * s];
+      int c = m[XCHG_META * s];
       c = c < 0 ? 0 : (c > x.cap ? x.cap : c);
       roff[s] = acc;
-      soff[s] = m[4 * s + 1];
+      soff[s] = m[XCHG_META * s + 1];
       acc += c;
     }
     roff[R] = acc;
@@ -183,11 +184,11 @@ __global__ void __launch_bounds__(256) k_xchg_gather_push(XchgDev x, const float
   }
   __syncthreads();
   if (overflow) {   // gradient inbox too small for this batch: the step becomes a no-op everywhere, error is sticky
-    if (blockIdx.x == 0 && threadIdx.x < R) x.meta[threadIdx.x][4 * me + 2] = -1;
+    if (blockIdx.x == 0 && threadIdx.x < R) x.meta[threadIdx.x][XCHG_META * me + 2] = -1;
     if (blockIdx.x == 0 && threadIdx.x == 0) { *n_dev = 0; x.flags[me][R] = 2; }
     return;
   }
-  if (blockIdx.x == 0 && threadIdx.x < R) x.meta[threadIdx.x][4 * me + 2] = roff[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x < R) x.meta[threadIdx.x][XCHG_META * me + 2] = roff[threadIdx.x];
   if (blockIdx.x == 0 && threadIdx.x == 0) *n_dev = roff[R];
   const int total = roff[R];
   const int lane = threadIdx.x & 31;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(256) k_xchg_grad_push(XchgDev x, const int32_t
     for (int r = 0; r < R; ++r) { off[r] = acc; acc += counts[r]; }
     off[R] = acc;
   }
-  if (threadIdx.x < R) base[threadIdx.x] = x.meta[me][4 * threadIdx.x + 2];
+  if (threadIdx.x < R) base[threadIdx.x] = x.meta[me][XCHG_META * threadIdx.x + 2];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(256) k_xchg_grad_push128(XchgDev x, const int3
     for (int r = 0; r < R; ++r) { off[r] = acc; acc += counts[r]; }
     off[R] = acc;
   }
-  if (threadIdx.x < R) base[threadIdx.x] = x.meta[me][4 * threadIdx.x + 2];
+  if (threadIdx.x < R) base[threadIdx.x] = x.meta[me][XCHG_META * threadIdx.x + 2];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -449,6 +450,45 @@ static int xchg_launch_grad(orx_handle_t h, int kind, const XchgDev& xd, const i
   return ORX_OK;
 }
 
+// (loss, l2) of the GLOBAL batch without a collective: every rank reduces its partials and stores the pair into every
+// peer's meta[me][4..5] (before barrier C); after the barrier each rank adds the R pairs it holds, in rank order, so all
+// ranks get bit-identical totals.
+__global__ void k_xchg_loss_push(XchgDev x, const float* partials, int n, float loss_scale) {
+  __shared__ double sh[2][256];
+  double l = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    l += (double)partials[2 * i];
+    q += (double)partials[2 * i + 1];
+  }
+  sh[0][threadIdx.x] = l;
+  sh[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < x.world) {
+    int32_t* m = x.meta[threadIdx.x] + XCHG_META * x.rank;
+    m[4] = __float_as_int((float)(sh[0][0] * (double)loss_scale));
+    m[5] = __float_as_int((float)(0.5 * sh[1][0]));
+  }
+}
+
+__global__ void k_xchg_loss_sum(XchgDev x, float* out4) {
+  if (threadIdx.x == 0) {
+    const int32_t* m = x.meta[x.rank];
+    float l = 0.f, q = 0.f;
+    for (int r = 0; r < x.world; ++r) {
+      l += __int_as_float(m[XCHG_META * r + 4]);
+      q += __int_as_float(m[XCHG_META * r + 5]);
+    }
+    out4[0] = l; out4[1] = q; out4[2] = 0.f; out4[3] = 0.f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // barrier over the ranks' streams: flags[r][me] = epoch at every peer, then wait for every peer's epoch in mine
 // ---------------------------------------------------------------------------------------
@@ -544,7 +584,8 @@ extern "C" int orx_xchg_barrier(orx_handle_t h, const void* xchg_host, int32_t e
   return ORX_OK;
 }
 
-// The whole step in one call (eight launches + three barriers, nothing returns to the host): see the file header.
+// The whole step in one call (nine launches + three barriers, nothing returns to the host): see the file header.
+// out4[0..1] = (loss, l2_loss) of the GLOBAL batch on every rank -- exchanged through the meta mailboxes, no collective.
 // work: int32[world + 1 + ceil(3B/1024) * world] scratch; slot: int32[3B]; req: int32[gin_rows]; epoch_base: the
 // barriers use epochs epoch_base+1..+3 (the caller advances it by 3 per step); gin_local: this rank's own gradient
 // inbox (the local address of gin[rank]).
@@ -564,6 +605,7 @@ extern "C" int orx_xchg_step(orx_handle_t h, int32_t kind, const void* xchg_host
   ORX_REQUIRE(epoch_base >= 0 && timeout_ms > 0, "bad epoch / timeout");
   ORX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)s;
+  if ((rc = orx_ensure_workspace(h, gin_rows, x->width, opt->kind == ORX_OPT_ADAM_DENSE))) return rc;
   const XchgDev xd = to_dev(x);
   const int R = x->world, nchunks = (3 * B + XCHG_CHUNK - 1) / XCHG_CHUNK;
   int32_t* counts = work;            // [R]
@@ -574,11 +616,23 @@ extern "C" int orx_xchg_step(orx_handle_t h, int32_t kind, const void* xchg_host
   k_xchg_scatter_push<<<nchunks, 256, 0, st>>>(xd, uid, pid, nid, B, total_users, bc, nchunks, counts, slot);
   k_xchg_barrier<<<1, XCHG_MAX_R, 0, st>>>(xd, epoch_base + 1, tmo);
   k_xchg_gather_push<<<h->num_sms * 8, 256, 0, st>>>(xd, tab->var, tab->rows, gin_rows, req, n_dev, nullptr);
+  // the owner's ids are final: build their batch index on the side stream while the gradient rows travel
+  if (!h->side_stream) {
+    ORX_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    ORX_CUDA(cudaEventCreateWithFlags(&h->side_ev[0], cudaEventDisableTiming));
+    ORX_CUDA(cudaEventCreateWithFlags(&h->side_ev[1], cudaEventDisableTiming));
+  }
+  ORX_CUDA(cudaEventRecord(h->side_ev[0], st));
+  ORX_CUDA(cudaStreamWaitEvent(h->side_stream, h->side_ev[0], 0));
+  if ((rc = orx_launch_index_build_strided(h, req, 1, tab->rows, gin_rows, n_dev, opt->kind == ORX_OPT_ADAM_DENSE, h->side_stream))) return rc;
+  ORX_CUDA(cudaEventRecord(h->side_ev[1], h->side_stream));
   k_xchg_barrier<<<1, XCHG_MAX_R, 0, st>>>(xd, epoch_base + 2, tmo);
   int np = 0;
   if ((rc = xchg_launch_grad(h, kind, xd, counts, slot, B, dim, margin, c_loss, c_l2, inv_B, st, &np))) return rc;
-  if ((rc = orx_launch_reduce_partials(h->partials, np, kind == ORX_PAIR_BPR ? inv_B : 1.f, out4, st))) return rc;
+  k_xchg_loss_push<<<1, 256, 0, st>>>(xd, h->partials, np, kind == ORX_PAIR_BPR ? inv_B : 1.f);
   k_xchg_barrier<<<1, XCHG_MAX_R, 0, st>>>(xd, epoch_base + 3, tmo);
+  k_xchg_loss_sum<<<1, 32, 0, st>>>(xd, out4);   // out4 = the GLOBAL (loss, l2_loss), identical on every rank
   ORX_LAUNCH_CHECK();
-  return orx_sparse_apply_devn(h, tab, req, gin_local, x->width, gin_rows, n_dev, opt, s);
+  ORX_CUDA(cudaStreamWaitEvent(st, h->side_ev[1], 0));
+  return orx_sparse_apply_prebuilt(h, tab, req, gin_local, x->width, gin_rows, n_dev, opt, st);
 }

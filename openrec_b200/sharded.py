@@ -146,7 +146,7 @@ class MailboxShardedPairwise(ShardedPairwise):
         dev = eng.device
         W = self.W
         self._bufs = [_PeerBuf(eng, (world * self.cap,), torch.int32),      # idbox
-                      _PeerBuf(eng, (world * 4,), torch.int32),             # meta
+                      _PeerBuf(eng, (world * 8,), torch.int32),             # meta
                       _PeerBuf(eng, (self.cap, W), torch.float32),          # got
                       _PeerBuf(eng, (self.gin_rows, W), torch.float32),     # gin
                       _PeerBuf(eng, (world + 1,), torch.int32)]             # flags
@@ -177,7 +177,7 @@ class MailboxShardedPairwise(ShardedPairwise):
         self._slot = torch.empty(self.cap, dtype=torch.int32, device=dev)
         self._out = torch.zeros(16, 4, dtype=torch.float32, device=dev)     # ring of step outputs (loss, l2, -, -)
         self.fused_call = os.environ.get("ORX_XCHG_FUSED", "1") != "0" and self.barrier_kind == "flag"
-        self.launches_per_step = 2 + 1 + 2 + 3 + 3   # hist, scatter+push, gather+push, grads+reduce, apply(3), 3 barriers
+        self.launches_per_step = 2 + 1 + 2 + 3 + 3 + 1   # hist, scatter+push, gather+push, grads+loss push, apply(3), 3 barriers, loss sum
         dist.barrier()
 
     def _barrier(self):
@@ -207,11 +207,7 @@ class MailboxShardedPairwise(ShardedPairwise):
                                              vp(self._slot), vp(self._req), self.margin, c_loss, c_l2, 1.0 / (B * R),
                                              C.byref(o), self._epoch, 5000, vp(out4), st), "orx_xchg_step")
             self._epoch += 3
-            out = out4[:2]
-            if reduce_loss:
-                out = out.clone()
-                dist.all_reduce(out)
-            return out
+            return out4[:2]        # already the global (loss, l2_loss): the partials travel through the mailboxes
         ids = torch.cat([uid, pid, nid])
         counts, send_local, slot = eng.owner_bucket_combined(ids, B, self.U, R)
         _lib.check(eng.lib.orx_xchg_push_ids(eng.h, x, vp(counts), vp(send_local), 3 * B, st), "orx_xchg_push_ids")
