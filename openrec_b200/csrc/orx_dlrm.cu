@@ -59,6 +59,25 @@ __device__ __forceinline__ bool inter_selected(int mode, int self, int i, int j)
   return mode == 0 ? (self ? j >= i : j > i) : (self ? j <= i : j < i);
 }
 
+// position of the selected entry (i,j) in the row-major enumeration of the selected entries
+__device__ __forceinline__ int inter_index(int mode, int self, int F, int i, int j) {
+  if (mode == 0) return self ? i * F - i * (i - 1) / 2 + (j - i) : i * (F - 1) - i * (i - 1) / 2 + (j - i - 1);
+  return self ? i * (i + 1) / 2 + j : i * (i - 1) / 2 + j;
+}
+
+// sample b's features -> shared memory, [F][D+1] (the +1 keeps same-column reads of different rows conflict-free)
+__device__ __forceinline__ void inter_load(const float* __restrict__ emb, int64_t emb_ld, const float* __restrict__ dense,
+                                           int64_t dense_ld, int b, int F, int D, float* sz) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5, Dp = D + 1;
+  for (int f = warp; f < F; f += nw) {
+    const float* src = f < F - 1 ? emb + (int64_t)b * emb_ld + (int64_t)f * D : dense + (int64_t)b * dense_ld;
+    for (int d = lane; d < D; d += 32) sz[f * Dp + d] = src[d];
+  }
+}
+
+// One CTA per sample.  The F x F cells are dealt to the threads; a selected cell is one D-long dot product out of
+// shared memory (first version: every thread walked all F*F cells with a runtime modulo per cell -- 10.4 ms at
+// B = 32768, F = 27, D = 128, profiles/r1v_dlrm_launches.csv).
 __global__ void __launch_bounds__(128) k_interact_fwd(const float* __restrict__ emb, int64_t emb_ld,
                                                       const float* __restrict__ dense, int64_t dense_ld, int B, int F,
                                                       int D, int self, int mode, float* __restrict__ out,
@@ -67,25 +86,26 @@ __global__ void __launch_bounds__(128) k_interact_fwd(const float* __restrict__ 
   const int b = blockIdx.x;
   if (b >= B) return;
   const int Dp = D + 1;
-  for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
-    const int f = e / D, d = e % D;
-    sz[f * Dp + d] = f < F - 1 ? emb[(int64_t)b * emb_ld + (int64_t)f * D + d] : dense[(int64_t)b * dense_ld + d];
-  }
+  inter_load(emb, emb_ld, dense, dense_ld, b, F, D, sz);
   __syncthreads();
-  // enumerate the selected (i,j) pairs row-major; thread t takes pairs t, t+blockDim, ...
-  int q = 0;
-  for (int i = 0; i < F; ++i)
-    for (int j = 0; j < F; ++j) {
-      if (!inter_selected(mode, self, i, j)) continue;
-      if ((q % blockDim.x) == threadIdx.x) {
-        float acc = 0.f;
-        if (mode == 1 || j == i) {  // mode 0: lower_tri(P)[i,j] with j>=i is non-zero only on the diagonal
-          for (int d = 0; d < D; ++d) acc += sz[i * Dp + d] * sz[j * Dp + d];
-        }
-        out[(int64_t)b * out_ld + q] = acc;
+  for (int c = threadIdx.x; c < F * F; c += blockDim.x) {
+    const int i = c / F, j = c - i * F;
+    if (!inter_selected(mode, self, i, j)) continue;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (mode == 1 || j == i) {  // mode 0: lower_tri(P)[i,j] with j>=i is non-zero only on the diagonal
+      const float* zi = sz + i * Dp;
+      const float* zj = sz + j * Dp;
+      int d = 0;
+      for (; d + 3 < D; d += 4) {
+        a0 += zi[d] * zj[d];
+        a1 += zi[d + 1] * zj[d + 1];
+        a2 += zi[d + 2] * zj[d + 2];
+        a3 += zi[d + 3] * zj[d + 3];
       }
-      ++q;
+      for (; d < D; ++d) a0 += zi[d] * zj[d];
     }
+    out[(int64_t)b * out_ld + inter_index(mode, self, F, i, j)] = (a0 + a1) + (a2 + a3);
+  }
 }
 
 // dZ = (dP + dP^T) Z restricted to the selected entries; emb part -> demb[b,f,:], dense part ADDED to ddense.
@@ -101,28 +121,23 @@ __global__ void __launch_bounds__(128) k_interact_bwd(const float* __restrict__ 
   const int Dp = D + 1;
   float* sz = sm;
   float* sp = sm + F * Dp;
-  for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
-    const int f = e / D, d = e % D;
-    sz[f * Dp + d] = f < F - 1 ? emb[(int64_t)b * emb_ld + (int64_t)f * D + d] : dense[(int64_t)b * dense_ld + d];
-  }
-  for (int e = threadIdx.x; e < F * F; e += blockDim.x) sp[e] = 0.f;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int q = 0;
-    for (int i = 0; i < F; ++i)
-      for (int j = 0; j < F; ++j) {
-        if (!inter_selected(mode, self, i, j)) continue;
-        if (mode == 1 || j == i) sp[i * F + j] = dout[(int64_t)b * dout_ld + q];
-        ++q;
-      }
+  inter_load(emb, emb_ld, dense, dense_ld, b, F, D, sz);
+  for (int c = threadIdx.x; c < F * F; c += blockDim.x) {
+    const int i = c / F, j = c - i * F;
+    float v = 0.f;
+    if (inter_selected(mode, self, i, j) && (mode == 1 || j == i))
+      v = dout[(int64_t)b * dout_ld + inter_index(mode, self, F, i, j)];
+    sp[c] = v;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
-    const int i = e / D, d = e % D;
-    float acc = 0.f;
-    for (int j = 0; j < F; ++j) acc += (sp[i * F + j] + sp[j * F + i]) * sz[j * Dp + d];
-    if (i < F - 1) demb[(int64_t)b * demb_ld + (int64_t)i * D + d] = acc;
-    else ddense[(int64_t)b * ddense_ld + d] += acc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < F; i += nw) {
+    for (int d = lane; d < D; d += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < F; ++j) acc += (sp[i * F + j] + sp[j * F + i]) * sz[j * Dp + d];
+      if (i < F - 1) demb[(int64_t)b * demb_ld + (int64_t)i * D + d] = acc;
+      else ddense[(int64_t)b * ddense_ld + d] += acc;
+    }
   }
 }
 
@@ -166,7 +181,7 @@ extern "C" int orx_interact_bwd(orx_handle_t h, const float* emb, int64_t emb_ld
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
                                               int64_t ldb, float* __restrict__ C, int64_t ldc, int M, int N, int K,
-                                              const float* __restrict__ bias, int act) {
+                                              const float* __restrict__ bias, int act, float* __restrict__ part) {
   constexpr int T = 64, KC = 16;
   __shared__ float sa[KC][T + 4], sb[KC][T + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -176,19 +191,22 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int64
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += KC) {
+  // split-K: blockIdx.z takes a KC-aligned slice of K and writes a raw partial tile (summed by k_splitk_reduce)
+  const int kper = ((K + (int)gridDim.z - 1) / (int)gridDim.z + KC - 1) / KC * KC;
+  const int k_lo = blockIdx.z * kper, k_hi = min(K, k_lo + kper);
+  for (int k0 = k_lo; k0 < k_hi; k0 += KC) {
     for (int e = threadIdx.x; e < T * KC; e += 256) {
       int r, k;
       if (TA == 0) { r = e / KC; k = e % KC; } else { k = e / T; r = e % T; }   // keep the global read contiguous
       float v = 0.f;
-      if (m0 + r < M && k0 + k < K) v = TA == 0 ? A[(int64_t)(m0 + r) * lda + k0 + k] : A[(int64_t)(k0 + k) * lda + m0 + r];
+      if (m0 + r < M && k0 + k < k_hi) v = TA == 0 ? A[(int64_t)(m0 + r) * lda + k0 + k] : A[(int64_t)(k0 + k) * lda + m0 + r];
       sa[k][r] = v;
     }
     for (int e = threadIdx.x; e < T * KC; e += 256) {
       int c, k;
       if (TB == 0) { k = e / T; c = e % T; } else { c = e / KC; k = e % KC; }
       float v = 0.f;
-      if (n0 + c < N && k0 + k < K) v = TB == 0 ? Bm[(int64_t)(k0 + k) * ldb + n0 + c] : Bm[(int64_t)(n0 + c) * ldb + k0 + k];
+      if (n0 + c < N && k0 + k < k_hi) v = TB == 0 ? Bm[(int64_t)(k0 + k) * ldb + n0 + c] : Bm[(int64_t)(n0 + c) * ldb + k0 + k];
       sb[k][c] = v;
     }
     __syncthreads();
@@ -214,6 +232,10 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int64
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx + 16 * j;
       if (n >= N) continue;
+      if (gridDim.z > 1) {
+        part[(size_t)blockIdx.z * (size_t)M * (size_t)N + (size_t)m * N + n] = acc[i][j];
+        continue;
+      }
       float v = acc[i][j] + (bias ? bias[n] : 0.f);
       if (act == 1) v = fmaxf(v, 0.f);
       else if (act == 2) v = orx_sigmoid(v);
@@ -224,6 +246,9 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, int64
 
 int orx_launch_gemm_tc(int TA, int TB, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc,
                        int M, int N, int K, const float* bias, int act, cudaStream_t st);   // orx_mlp_tc.cu
+float* orx_splitk_workspace(size_t floats);                                                  // orx_mlp_tc.cu
+int orx_launch_splitk_reduce(const float* part, int S, int M, int N, float* C, int64_t ldc, const float* bias, int act,
+                             cudaStream_t st);
 
 // ORX_MLP_SIMT=1 forces the fp32 SIMT tiles (the reference the tcgen05 path is checked against in the tests)
 static bool mlp_use_tc() {
@@ -242,9 +267,22 @@ static int launch_gemm(const float* A, int64_t lda, const float* Bm, int64_t ldb
     const int rc = orx_launch_gemm_tc(TA, TB, A, lda, Bm, ldb, C, ldc, M, N, K, bias, act, st);
     if (rc != ORX_ERR_UNSUPPORTED) return rc;
   }
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  k_gemm<TA, TB><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, C, ldc, M, N, K, bias, act);
+  const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
+  int S = 1;
+  if (tiles < 148 && K >= 1024) {   // dw of a narrow layer (13 x 512, 256 x 1): K = batch, a handful of tiles
+    S = (2 * 148 + tiles - 1) / tiles;
+    if (S > K / 256) S = K / 256;
+    if (S > 65535) S = 65535;
+  }
+  float* part = nullptr;
+  if (S > 1) {
+    part = orx_splitk_workspace((size_t)S * (size_t)M * (size_t)N);
+    if (!part) { orx_set_error("split-K workspace allocation failed"); return ORX_ERR_CUDA; }
+  }
+  dim3 grid((N + 63) / 64, (M + 63) / 64, S);
+  k_gemm<TA, TB><<<grid, 256, 0, st>>>(A, lda, Bm, ldb, C, ldc, M, N, K, bias, act, part);
   ORX_LAUNCH_CHECK();
+  if (S > 1) return orx_launch_splitk_reduce(part, S, M, N, C, ldc, bias, act, st);
   return ORX_OK;
 }
 
@@ -272,19 +310,22 @@ __global__ void k_act_bwd(const float* __restrict__ y, int64_t ldy, float* __res
 }
 
 __global__ void __launch_bounds__(256) k_col_sum(const float* __restrict__ dz, int64_t ld, int B, int N,
-                                                 float* __restrict__ db) {
-  // block (32 cols x 8 row-lanes); deterministic: fixed row partition, smem tree
+                                                 float* __restrict__ out) {
+  // block (32 cols x 8 row-lanes) over the row slice blockIdx.y; deterministic: fixed row partition, smem tree;
+  // out = db when gridDim.y == 1, else the partial [gridDim.y][N] summed by k_splitk_reduce
   __shared__ float sh[8][33];
   const int n = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+  const int per = (B + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int b_lo = blockIdx.y * per, b_hi = min(B, b_lo + per);
   float acc = 0.f;
   if (n < N)
-    for (int b = r; b < B; b += 8) acc += dz[(int64_t)b * ld + n];
+    for (int b = b_lo + r; b < b_hi; b += 8) acc += dz[(int64_t)b * ld + n];
   sh[r][threadIdx.x & 31] = acc;
   __syncthreads();
   if (r == 0 && n < N) {
     float t = 0.f;
     for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x & 31];
-    db[n] = t;
+    out[(size_t)blockIdx.y * N + n] = t;
   }
 }
 
@@ -303,8 +344,23 @@ extern "C" int orx_mlp_layer_bwd(orx_handle_t h, const float* x, int64_t ldx, co
     ORX_LAUNCH_CHECK();
   }
   if (db) {
-    k_col_sum<<<(out + 31) / 32, 256, 0, st>>>(dy, lddy, B, out, db);
-    ORX_LAUNCH_CHECK();
+    const int cb = (out + 31) / 32;
+    int S = 1;
+    if (B >= 4096) {
+      S = (2 * 148 + cb - 1) / cb;
+      if (S > B / 256) S = B / 256;
+    }
+    if (S > 1) {
+      float* part = orx_splitk_workspace((size_t)S * (size_t)out);
+      if (!part) { orx_set_error("split workspace allocation failed"); return ORX_ERR_CUDA; }
+      k_col_sum<<<dim3(cb, S), 256, 0, st>>>(dy, lddy, B, out, part);
+      ORX_LAUNCH_CHECK();
+      const int rc2 = orx_launch_splitk_reduce(part, S, 1, out, db, out, nullptr, 0, st);
+      if (rc2) return rc2;
+    } else {
+      k_col_sum<<<cb, 256, 0, st>>>(dy, lddy, B, out, db);
+      ORX_LAUNCH_CHECK();
+    }
   }
   int rc = launch_gemm<1, 0>(x, ldx, dy, lddy, dw, out, in, out, B, nullptr, 0, st);   // dw = x^T dz
   if (rc) return rc;
