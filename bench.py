@@ -44,11 +44,16 @@ ALG_BYTES_PER_TRIPLET = 12 + 4 * (3 * D + 2) * (2 + 2 * 1)
 
 
 def workload_name(n_gpus):
-    s = (f"BPR {U} users x {I} items, dim {D}, batch {B} per GPU, Adagrad lr {LR} (acc init 0.1), "
+    items = I if n_gpus == 1 else 12_500_000 * n_gpus          # BASELINE configs[1] / configs[4] (100M items on 8 GPUs)
+    s = (f"BPR {U} users x {items} items, dim {D}, batch {B} per GPU, Adagrad lr {LR} (acc init 0.1), "
          f"ids uniform i.i.d. int32, {N_BATCHES} rotating id batches")
     if n_gpus > 1:
-        s += (f", 1M users + 12.5M items per GPU row-sharded over {n_gpus} GPUs (row r on rank r % N), "
-              "NCCL all-to-all exchange of ids / rows / gradient rows")
+        mode = os.environ.get("ORX_SHARDED", "mailbox")
+        how = {"mailbox": "liborx kernels store ids / rows / gradient rows into the peers' IPC-mapped mailboxes over NVLink "
+                          "(no collective in the step)",
+               "peer": "one-sided peer loads / stores on the mapped shards"}.get(
+                   mode, "NCCL all-to-all exchange of counts / ids / rows / gradient rows")
+        s += f", user and item tables row-sharded over {n_gpus} GPUs (row r on rank r % N, 12.5M item rows per GPU); {how}"
     return s
 
 
@@ -171,7 +176,8 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(1), "note": "CPU restatement of openrec.tf2 (TensorFlow not "
-                       "installable): oracle/c/orx_oracle.c, all host threads"},
+                       "installable): oracle/c/orx_oracle.c, all host threads; always the single-GPU workload (1M x 1M): "
+                       "the reference has no multi-device path and the 100M-item tables need ~100 GB of host memory"},
             "cpu_baseline": {"value": v, "unit": UNIT, **info},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -216,8 +222,10 @@ def run_b200(args, rank, world, local_rank):
                 "warmup": args.warmup, "ms_per_step": result["seconds"] / K * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(world), "optimizer": "Adagrad (Keras sparse semantics)",
-                           "l2_flush": "none needed: tables+accumulators 2.06 GB per GPU and a 406 MB/step random "
-                                       "working set >> 126 MB L2",
+                           "l2_flush": ("none needed: tables+accumulators 2.06 GB per GPU and a 406 MB/step random "
+                                        "working set >> 126 MB L2") if world == 1 else
+                                       ("none needed: 13.3 GB of table + accumulator per GPU, 0.3 GB of mailbox traffic and "
+                                        "0.4 GB of random row updates per step >> 126 MB L2"),
                            "parallelism": "single GPU" if world == 1 else f"row-sharded tables x{world}"},
                 "clocks": result["clocks"],
                 "e2e": {"value": units / result["e2e_seconds"], "unit": UNIT,
