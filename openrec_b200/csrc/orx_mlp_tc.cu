@@ -460,19 +460,22 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
 
 }  // namespace
 
-// split-K workspace, one per process (a process drives one device); grown on demand
-static float* g_part = nullptr;
-static size_t g_part_floats = 0;
+// split-K workspace: one buffer per device (indexed by the current device), grown on demand, reused by every GEMM /
+// column sum of that device's stream in order
+static float* g_part[64] = {nullptr};
+static size_t g_part_floats[64] = {0};
 float* orx_splitk_workspace(size_t floats) {
-  if (floats > g_part_floats) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (floats > g_part_floats[dev]) {
     cudaDeviceSynchronize();
-    cudaFree(g_part);
-    g_part = nullptr;
-    g_part_floats = 0;
-    if (cudaMalloc(&g_part, sizeof(float) * floats) != cudaSuccess) return nullptr;
-    g_part_floats = floats;
+    cudaFree(g_part[dev]);
+    g_part[dev] = nullptr;
+    g_part_floats[dev] = 0;
+    if (cudaMalloc(&g_part[dev], sizeof(float) * floats) != cudaSuccess) return nullptr;
+    g_part_floats[dev] = floats;
   }
-  return g_part;
+  return g_part[dev];
 }
 int orx_launch_splitk_reduce(const float* part, int S, int M, int N, float* C, int64_t ldc, const float* bias, int act, cudaStream_t st) {
   const int64_t n = (int64_t)M * N;

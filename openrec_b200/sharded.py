@@ -20,10 +20,12 @@ arithmetic op is a liborx kernel reached through ``eng``.
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import os
 import time
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -132,10 +134,6 @@ class MailboxShardedPairwise(ShardedPairwise):
 
     def __init__(self, eng, rank, world, total_users, total_items, dim, batch, *, barrier=None, gin_rows=None, **kw):
         super().__init__(eng, rank, world, total_users, total_items, dim, **kw)
-        import ctypes as C
-
-        import numpy as np
-
         from .sharded_peer import _PeerBuf
         if dim % 4:
             raise ValueError("the mailbox exchange needs dim % 4 == 0")
@@ -181,7 +179,6 @@ class MailboxShardedPairwise(ShardedPairwise):
         dist.barrier()
 
     def _barrier(self):
-        import ctypes as C
         if self.barrier_kind == "flag":
             self._epoch += 1
             _lib.check(self.eng.lib.orx_xchg_barrier(self.eng.h, C.byref(self._x), self._epoch, 5000, self.eng.stream()),
@@ -190,7 +187,6 @@ class MailboxShardedPairwise(ShardedPairwise):
             dist.all_reduce(self._flag)
 
     def step(self, uid, pid, nid, c_loss=1.0, c_l2=1.0, reduce_loss=True):
-        import ctypes as C
         eng, R, D, W = self.eng, self.world, self.D, self.W
         B = uid.numel()
         if B > self.B:
@@ -237,7 +233,6 @@ class MailboxShardedPairwise(ShardedPairwise):
                                 2: "gradient inbox overflow: rebuild with a larger gin_rows"}.get(code, f"error {code}"))
 
     def close(self):
-        import ctypes as C
         torch.cuda.synchronize()
         dist.barrier()
         for p in self._opened:
