@@ -29,17 +29,35 @@ static void* scratch(int slot, size_t bytes) {
   return buf[slot];
 }
 
-static int cmp_u64(const void* a, const void* b) {
-  uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
-  return (x > y) - (x < y);
+/* stable LSD radix sort of (id << 32 | position) keys by id, 11 bits per pass: the dedup of TF's IndexedSlices
+ * aggregation (unique + segment sum, batch order inside a segment).  qsort with a comparison callback took a third
+ * of the step on its own and does not scale with threads -- the CPU baseline should not be a strawman. */
+static void radix_sort_by_id(uint64_t* key, uint64_t* tmp, int n, int64_t max_id) {
+  int bits = 1;
+  while (bits < 32 && ((int64_t)1 << bits) <= max_id) ++bits;
+  uint64_t *src = key, *dst = tmp;
+  for (int shift = 0; shift < bits; shift += 11) {
+    size_t hist[2049];
+    memset(hist, 0, sizeof(hist));
+    for (int i = 0; i < n; ++i) ++hist[((src[i] >> (32 + shift)) & 2047u) + 1];
+    for (int b = 0; b < 2048; ++b) hist[b + 1] += hist[b];
+    for (int i = 0; i < n; ++i) dst[hist[(src[i] >> (32 + shift)) & 2047u]++] = src[i];
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  if (src != key) memcpy(key, src, sizeof(uint64_t) * (size_t)n);
 }
 
 /* dedup + apply: indices[n], values[n,D] -> per unique row: G = sum (batch order); opt: 0 SGD, 1 Adagrad */
 static void sparse_apply(float* var, float* acc, int D, const int32_t* idx, const float* val, int n, int opt,
                          float lr, float eps) {
   uint64_t* key = (uint64_t*)scratch(0, sizeof(uint64_t) * (size_t)n);
-  for (int i = 0; i < n; ++i) key[i] = ((uint64_t)(uint32_t)idx[i] << 32) | (uint32_t)i;
-  qsort(key, (size_t)n, sizeof(uint64_t), cmp_u64);
+  uint64_t* tmp = (uint64_t*)scratch(6, sizeof(uint64_t) * (size_t)n);
+  int32_t max_id = 0;
+  for (int i = 0; i < n; ++i) {
+    key[i] = ((uint64_t)(uint32_t)idx[i] << 32) | (uint32_t)i;
+    if (idx[i] > max_id) max_id = idx[i];
+  }
+  radix_sort_by_id(key, tmp, n, max_id);
   int* seg = (int*)scratch(1, sizeof(int) * (size_t)(n + 1));
   int ns = 0;
   for (int i = 0; i < n; ++i)
