@@ -38,6 +38,7 @@ struct OrxHash {
   int32_t* didx;              // [cap]  compact staging index of a staged row
   int32_t* did;               // [cap_rows] row id of staging index d
   int32_t* counter;           // number of staged rows
+  unsigned long long* cnt;    // [cap]  (epoch << 32 | references) of a duplicated row -- "last arriver applies" variant only
   uint32_t mask;
   int32_t shift;  // 32 - log2(cap)
   uint32_t epoch;  // current epoch, >= 1
@@ -109,7 +110,8 @@ __device__ __forceinline__ unsigned long long orx_slot_word(uint32_t epoch, int3
 }
 
 // Insert one id.  mode 0: rows get a staging index when they are seen the SECOND time (duplicates only);
-// mode 1: on the FIRST occurrence (ADAM_DENSE stages every row); mode 2: never (pure dedup, censor).
+// mode 1: on the FIRST occurrence (ADAM_DENSE stages every row); mode 2: never (pure dedup, censor);
+// mode 3: as mode 0, and every repeat is counted in cnt[slot] (total references of a duplicated row).
 // Returns 0 if this call was the first occurrence of the id in this epoch, else 1.
 __device__ __forceinline__ uint32_t orx_hash_insert(const OrxHash& t, int32_t id, int mode) {
   const unsigned long long mine = orx_slot_word(t.epoch, id);
@@ -129,9 +131,21 @@ __device__ __forceinline__ uint32_t orx_hash_insert(const OrxHash& t, int32_t id
       w = old;                              // somebody else claimed it meanwhile (same epoch by construction)
     }
     if ((w & ~ORX_DUP_BIT) == mine) {
+      if (mode == 3) {   // reference count of a duplicated row: the first repeat sets (epoch, 2), later ones add 1
+        const unsigned long long fresh = ((unsigned long long)t.epoch << 32) | 2ull;
+        while (true) {
+          const unsigned long long c = __ldcg(t.cnt + h);
+          if ((uint32_t)(c >> 32) != t.epoch) {
+            if (atomicCAS(t.cnt + h, c, fresh) == c) break;
+          } else {
+            atomicAdd(t.cnt + h, 1ull);
+            break;
+          }
+        }
+      }
       if (!(w & ORX_DUP_BIT)) {
         const unsigned long long old = atomicOr(t.slots + h, ORX_DUP_BIT);
-        if (mode == 0 && !(old & ORX_DUP_BIT)) {   // this call made the row "shared": give it a staging slot
+        if ((mode == 0 || mode == 3) && !(old & ORX_DUP_BIT)) {   // this call made the row "shared": give it a staging slot
           const int d = atomicAdd(t.counter, 1);
           t.didx[h] = d;
           t.did[d] = id;
@@ -156,6 +170,26 @@ __device__ __forceinline__ uint32_t orx_hash_find(const OrxHash& t, int32_t id, 
     }
     if ((uint32_t)(w >> 33) != t.epoch) {
       *d = -1;
+      return 0u;
+    }
+    h = (h + 1) & t.mask;
+  }
+}
+
+// orx_hash_find that also returns the slot index (for cnt[slot])
+__device__ __forceinline__ uint32_t orx_hash_find_slot(const OrxHash& t, int32_t id, int32_t* d, int32_t* slot) {
+  const unsigned long long mine = orx_slot_word(t.epoch, id);
+  uint32_t h = orx_hash32((uint32_t)id, t.shift);
+  while (true) {
+    const unsigned long long w = __ldg(t.slots + h);
+    if ((w & ~ORX_DUP_BIT) == mine) {
+      *d = __ldg(t.didx + h);
+      *slot = (int32_t)h;
+      return (w & ORX_DUP_BIT) ? 2u : 1u;
+    }
+    if ((uint32_t)(w >> 33) != t.epoch) {
+      *d = -1;
+      *slot = -1;
       return 0u;
     }
     h = (h + 1) & t.mask;
@@ -264,4 +298,5 @@ int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t ro
 int orx_ensure_partials(orx_ctx* c, int need, cudaStream_t st);
 int orx_launch_reduce_partials(const float* partials, int n, float loss_scale, float* out4, cudaStream_t st);
 int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
-                           const int32_t* b1, int64_t rows_b, int32_t nb, bool stage_all, cudaStream_t st);
+                           const int32_t* b1, int64_t rows_b, int32_t nb, int mode /* orx_hash_insert mode: 0 | 1 | 3 */,
+                           cudaStream_t st);

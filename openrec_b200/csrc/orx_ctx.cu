@@ -27,6 +27,8 @@ static void free_hash(OrxHash& t) {
   cudaFree(t.slots);
   cudaFree(t.didx);
   cudaFree(t.did);
+  cudaFree(t.cnt);
+  t.cnt = nullptr;
   t.slots = nullptr;
   t.didx = nullptr;
   t.did = nullptr;
@@ -62,7 +64,9 @@ static int alloc_hash(OrxHash& t, int64_t lookups, int32_t* counter) {
   ORX_CUDA(cudaMalloc(&t.slots, sizeof(unsigned long long) * cap));
   ORX_CUDA(cudaMalloc(&t.didx, sizeof(int32_t) * cap));
   ORX_CUDA(cudaMalloc(&t.did, sizeof(int32_t) * (lookups + 1)));
+  ORX_CUDA(cudaMalloc(&t.cnt, sizeof(unsigned long long) * cap));
   ORX_CUDA(cudaMemset(t.slots, 0, sizeof(unsigned long long) * cap));
+  ORX_CUDA(cudaMemset(t.cnt, 0, sizeof(unsigned long long) * cap));
   return ORX_OK;
 }
 

@@ -27,6 +27,18 @@ __global__ void k_index_build(OrxHash hu, OrxHash hi, const int32_t* __restrict_
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = na + (b1 ? 2 * nb : nb);
   if (i >= total) return;
+  if (stage_all == 3) {
+    // reference-counting mode (pairwise only: na == nb, b1 != 0): a triplet with ANY id out of range is skipped as a
+    // whole by k_pair_step, so none of its ids may be counted -- the counts must equal the decrements
+    const int tq = i < na ? i : (i - na < nb ? i - na : i - na - nb);
+    const int32_t x = a[tq], y = b0[tq], z = b1[tq];
+    const bool ok = x >= 0 && (int64_t)x < rows_a && y >= 0 && (int64_t)y < rows_b && z >= 0 && (int64_t)z < rows_b;
+    const int32_t id = i < na ? x : (i - na < nb ? y : z);
+    const bool mine_ok = id >= 0 && (int64_t)id < (i < na ? rows_a : rows_b);
+    if (!mine_ok) atomicAdd(bad, 1);
+    if (ok) orx_hash_insert(i < na ? hu : hi, id, 3);
+    return;
+  }
   if (i < na) {
     const int32_t id = a[i];
     if (id >= 0 && (int64_t)id < rows_a) orx_hash_insert(hu, id, stage_all);
@@ -61,12 +73,12 @@ int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride,
 }
 
 int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
-                           const int32_t* b1, int64_t rows_b, int32_t nb, bool stage_all, cudaStream_t st) {
+                           const int32_t* b1, int64_t rows_b, int32_t nb, int mode, cudaStream_t st) {
   const int total = na + (b1 ? 2 * nb : nb);
   if (total <= 0) return ORX_OK;
   orx_new_epoch(c);
-  k_index_build<<<(total + 255) / 256, 256, 0, st>>>(c->hu, c->hi, a, rows_a, na, b0, b1, rows_b, nb,
-                                                    stage_all ? 1 : 0, c->counters + 3);
+  k_index_build<<<(total + 255) / 256, 256, 0, st>>>(c->hu, c->hi, a, rows_a, na, b0, b1, rows_b, nb, mode,
+                                                    c->counters + 3);
   ORX_LAUNCH_CHECK();
   return ORX_OK;
 }
@@ -80,6 +92,7 @@ struct TripRegs {
   float4 us0[K], ps0[K], ns0[K];  // dead arrays are eliminated when the optimizer has no such slot
   float4 us1[K], ps1[K], ns1[K];
   int fl, uu, pp, nn, du, dp, dn;
+  int su, sp, sn;  // hash slot of the row (reference counter), LA variant only
   float bp, bn;
 };
 
@@ -89,7 +102,12 @@ struct TripRegs {
 //   ids (coalesced, lanes < CH) -> variable rows of the first one/two triplet groups (they need only
 //   the ids) -> hash probes + bias loads (lanes < CH, overlap the row loads) -> slot rows of the first
 //   groups -> steady state: process one register buffer while the other's 128-bit loads are in flight.
-template <int KIND, int OPT, int D, int CH, int MINB, bool PIPE>
+// LA ("last arriver applies", ORX_PAIR_VARIANT=7/8, experimental): shared rows carry a reference count built by
+// k_index_build (mode 3).  After a triplet has RED-added its gradient for a shared row it decrements the count; the
+// contributor that takes it to zero applies the optimizer to that row on the spot.  Every other reader's load of the
+// row precedes that reader's own decrement, so all gathers still see pre-step values, and the tail launch disappears
+// (loss reduction + counter reset move to a last-block-done epilogue).  DESIGN.md section 10.1.
+template <int KIND, int OPT, int D, int CH, int MINB, bool PIPE, bool LA = false>
 __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
   constexpr int G = (D / 4 < 32) ? D / 4 : 32;  // lanes per triplet
   constexpr int K = D / (4 * G);                // float4 per lane per row
@@ -136,10 +154,18 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
 
   // ---- hash probes + item_bias (lanes < CH), overlapping the row loads above
   float bp = 0.f, bn = 0.f, bps0 = 0.f, bps1 = 0.f, bns0 = 0.f, bns1 = 0.f;
+  int hsu = -1, hsp = -1, hsn = -1;
   if (flags & 1) {
-    const uint32_t cu = orx_hash_find(a.hu, u_id, &du);
-    const uint32_t cp = orx_hash_find(a.hi, p_id, &dp);
-    const uint32_t cn = orx_hash_find(a.hi, n_id, &dn);
+    uint32_t cu, cp, cn;
+    if constexpr (LA) {
+      cu = orx_hash_find_slot(a.hu, u_id, &du, &hsu);
+      cp = orx_hash_find_slot(a.hi, p_id, &dp, &hsp);
+      cn = orx_hash_find_slot(a.hi, n_id, &dn, &hsn);
+    } else {
+      cu = orx_hash_find(a.hu, u_id, &du);
+      cp = orx_hash_find(a.hi, p_id, &dp);
+      cn = orx_hash_find(a.hi, n_id, &dn);
+    }
     bp = __ldcg(a.Bv + p_id);
     bn = __ldcg(a.Bv + n_id);
     if (!STAGE_ONLY) {
@@ -164,6 +190,11 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
     r.dn = __shfl_sync(ORX_FULL, dn, src);
     r.bp = __shfl_sync(ORX_FULL, bp, src);
     r.bn = __shfl_sync(ORX_FULL, bn, src);
+    if constexpr (LA) {
+      r.su = __shfl_sync(ORX_FULL, hsu, src);
+      r.sp = __shfl_sync(ORX_FULL, hsp, src);
+      r.sn = __shfl_sync(ORX_FULL, hsn, src);
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int off = (k * G + gl) * 4;
@@ -243,6 +274,59 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
           orx_red4(a.gi + (int64_t)r.dn * D + off, gn);
         }
       }
+      if constexpr (LA && !STAGE_ONLY) {
+        const int shared = (~r.fl) & 14;   // rows of this triplet that went to the staging buffers
+        if (shared) {
+          // bias contributions of shared item rows must be in before the reference is given back
+          if (gl == 0) {
+            if (shared & 4) atomicAdd(a.gb + r.dp, gbias);
+            if (shared & 8) atomicAdd(a.gb + r.dn, -gbias);
+          }
+          __threadfence();                 // my REDs / atomics are visible before my decrements
+          int last = 0;
+          if (gl == 0) {
+            if ((shared & 2) && (uint32_t)atomicAdd(a.hu.cnt + r.su, ~0ull) == 1u) last |= 2;
+            if ((shared & 4) && (uint32_t)atomicAdd(a.hi.cnt + r.sp, ~0ull) == 1u) last |= 4;
+            if ((shared & 8) && (uint32_t)atomicAdd(a.hi.cnt + r.sn, ~0ull) == 1u) last |= 8;
+          }
+          last = __shfl_sync(ORX_FULL, last, grp * G);
+          if (last) {
+            __threadfence();               // every contributor's REDs happened before its decrement, hence before mine
+            auto apply_row = [&](float* W, float* P0, float* P1, float* stage, int id, int d, const float4* cur) {
+#pragma unroll
+              for (int k = 0; k < K; ++k) {
+                const int off = (k * G + gl) * 4;
+                const int64_t o = (int64_t)id * D + off;
+                float* sp_ = stage + (int64_t)d * D + off;
+                const float4 gs = __ldcg(reinterpret_cast<const float4*>(sp_));
+                float4 s0v = S0 ? __ldcg(reinterpret_cast<const float4*>(P0 + o)) : z4;
+                float4 s1v = S1 ? __ldcg(reinterpret_cast<const float4*>(P1 + o)) : z4;
+                __stcg(reinterpret_cast<float4*>(W + o), orx_apply4<OPT>(cur[k], gs, s0v, s1v, a.opt));
+                if (S0) __stcg(reinterpret_cast<float4*>(P0 + o), s0v);
+                if (S1) __stcg(reinterpret_cast<float4*>(P1 + o), s1v);
+                __stcg(reinterpret_cast<float4*>(sp_), z4);
+              }
+            };
+            auto apply_bias = [&](int id, int d) {   // item rows only; one lane
+              const float gbv = __ldcg(a.gb + d);
+              float s0v = S0 ? __ldcg(a.Bs0 + id) : 0.f, s1v = S1 ? __ldcg(a.Bs1 + id) : 0.f;
+              __stcg(a.Bv + id, orx_apply<OPT>(__ldcg(a.Bv + id), gbv, s0v, s1v, a.opt));
+              if (S0) __stcg(a.Bs0 + id, s0v);
+              if (S1) __stcg(a.Bs1 + id, s1v);
+              __stcg(a.gb + d, 0.f);
+            };
+            if (last & 2) apply_row(a.U, a.Us0, a.Us1, a.gu, r.uu, r.du, r.u);
+            if (last & 4) {
+              apply_row(a.I, a.Is0, a.Is1, a.gi, r.pp, r.dp, r.p);
+              if (gl == 0) apply_bias(r.pp, r.dp);
+            }
+            if (last & 8) {
+              apply_row(a.I, a.Is0, a.Is1, a.gi, r.nn, r.dn, r.n);
+              if (gl == 0) apply_bias(r.nn, r.dn);
+            }
+          }
+        }
+      }
     }
   };
 
@@ -279,14 +363,14 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
       __stcg(a.Bv + p_id, orx_apply<OPT>(bp, g_own, bps0, bps1, a.opt));
       if (S0) __stcg(a.Bs0 + p_id, bps0);
       if (S1) __stcg(a.Bs1 + p_id, bps1);
-    } else {
+    } else if (!LA || STAGE_ONLY) {
       atomicAdd(a.gb + dp, g_own);
     }
     if (flags & 8) {
       __stcg(a.Bv + n_id, orx_apply<OPT>(bn, -g_own, bns0, bns1, a.opt));
       if (S0) __stcg(a.Bs0 + n_id, bns0);
       if (S1) __stcg(a.Bs1 + n_id, bns1);
-    } else {
+    } else if (!LA || STAGE_ONLY) {
       atomicAdd(a.gb + dn, -g_own);
     }
     if (a.g_out) a.g_out[t] = (KIND == ORX_PAIR_BPR) ? g_own : -g_own;
@@ -312,6 +396,41 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
     }
     a.partials[2 * blockIdx.x] = l;
     a.partials[2 * blockIdx.x + 1] = q;
+  }
+  if constexpr (LA) {
+    // last block done: deterministic (fixed order, double) reduction of the per-block partials, out4, counter reset
+    __shared__ bool is_last;
+    __shared__ double dred[2][256];
+    if (threadIdx.x == 0) {
+      __threadfence();
+      is_last = (atomicAdd(a.counters + 2, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      double l = 0.0, q = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        l += (double)__ldcg(a.partials + 2 * i);
+        q += (double)__ldcg(a.partials + 2 * i + 1);
+      }
+      dred[0][threadIdx.x] = l;
+      dred[1][threadIdx.x] = q;
+      __syncthreads();
+      for (int sft = 128; sft > 0; sft >>= 1) {
+        if (threadIdx.x < sft) {
+          dred[0][threadIdx.x] += dred[0][threadIdx.x + sft];
+          dred[1][threadIdx.x] += dred[1][threadIdx.x + sft];
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) {
+        a.out4[0] = (float)(dred[0][0] * (double)a.loss_scale);
+        a.out4[1] = (float)(0.5 * dred[1][0]);
+        a.out4[2] = (float)a.counters[3];
+        a.out4[3] = (float)(a.counters[0] + a.counters[1]);
+        a.counters[0] = a.counters[1] = a.counters[2] = a.counters[3] = 0;
+      }
+    }
   }
 }
 
@@ -893,6 +1012,14 @@ static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaS
         case 4: go_async(k_pair_step_async<KIND, OPT, 128, 8, 2, 4>, 8, 4); break;
         case 5: go_async(k_pair_step_async<KIND, OPT, 128, 8, 3, 3>, 8, 3); break;
         case 6: go_async(k_pair_step_async<KIND, OPT, 128, 8, 4, 2>, 8, 2); break;
+        case 7:   // last arriver applies (pa.out4 is set only when the caller built the counting index), 4 CTAs/SM
+          if (pa.out4) go(k_pair_step<KIND, OPT, 128, 8, 4, false, true>, 8);
+          else go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8);
+          break;
+        case 8:   // same, 3 CTAs/SM (85 registers)
+          if (pa.out4) go(k_pair_step<KIND, OPT, 128, 8, 3, false, true>, 8);
+          else go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8);
+          break;
         default: go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8); break;
       }
       break;
@@ -978,7 +1105,10 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
     }
     if (rc != ORX_ERR_UNSUPPORTED) return rc;
   }
-  if ((rc = orx_launch_index_build(c, uid, user->rows, B, pid, nid, item->rows, B, dense, st))) return rc;
+  // experimental "last arriver applies" variants (D = 128, not Keras-dense Adam): reference-counted index, no tail
+  const bool la = D == 128 && !dense && opt->kind != ORX_OPT_ADAM_LAZY && (pair_variant() == 7 || pair_variant() == 8);
+  pa.out4 = la ? out4 : nullptr; pa.counters = c->counters; pa.loss_scale = (kind == ORX_PAIR_BPR) ? pa.inv_B : 1.0f;
+  if ((rc = orx_launch_index_build(c, uid, user->rows, B, pid, nid, item->rows, B, la ? 3 : (dense ? 1 : 0), st))) return rc;
   orx_prof_mark(c, 1, st);
   pa.hu = c->hu; pa.hi = c->hi;
   int n_partials = 0;
@@ -986,6 +1116,11 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
                               : launch_pair_step_kind<ORX_PAIR_UCML>(pa, opt->kind, st, &n_partials);
   if (rc) return rc;
   orx_prof_mark(c, 2, st);
+  if (la) {   // the step kernel's own epilogue wrote out4 and reset the counters
+    orx_prof_mark(c, 3, st);
+    orx_prof_next(c);
+    return ORX_OK;
+  }
   if (dense) {
     if ((rc = orx_launch_adam_sweep(c, user->var, user->s0, user->s1, user->rows, D, c->hu, c->gu, pa.opt, st))) return rc;
     if ((rc = orx_launch_adam_sweep(c, item->var, item->s0, item->s1, item->rows, D, c->hi, c->gi, pa.opt, st))) return rc;
