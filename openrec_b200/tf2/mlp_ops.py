@@ -3,9 +3,21 @@ DLRM forward/backward composition -- all arithmetic in liborx (orx_mlp_layer_*, 
 orx_gather_strided, orx_pred_loss); this module only sequences launches and owns activations."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import native as N
+
+# ORX_DLRM_PAD=1 (experimental): give (dense_vec | interactions) and its gradient a leading dimension that is a multiple
+# of 4 floats, so that every row of the 479-wide top-MLP input is 16-byte aligned (128-bit loads / cp.async in the
+# Dense-layer kernels).  The kernels take explicit leading dimensions, nothing else changes.
+_PAD = os.environ.get("ORX_DLRM_PAD", "0") == "1"
+
+
+def _rows(B, n, device):
+    ld = (n + 3) // 4 * 4 if _PAD else n
+    return torch.empty(B, ld, dtype=torch.float32, device=device)[:, :n]
 
 ACT = {None: 0, "linear": 0, "relu": 1, "sigmoid": 2}
 
@@ -50,7 +62,7 @@ class DLRMGraph:
         Z = c["Z"] = torch.empty(B, T, D, dtype=torch.float32, device=dev)
         for k, tab in enumerate(self.tables):                        # dlrm.py:83-85
             eng.gather_strided(tab, sparse, k, Z[:, k, :])
-        top_in = c["top_in"] = torch.empty(B, D + P, dtype=torch.float32, device=dev)
+        top_in = c["top_in"] = _rows(B, D + P, dev)
         x, acts = dense, []
         for l, (w, b, act) in enumerate(self.bot):                   # dlrm.py:87
             last = l == len(self.bot) - 1
@@ -84,7 +96,7 @@ class DLRMGraph:
         B, D = dense.shape[0], self.D
         dev = dense.device
         dy = c["dpred"].reshape(B, 1)
-        d_top_in = torch.empty_like(top_in)
+        d_top_in = _rows(B, top_in.shape[1], dev)
         top_g = [None] * len(self.top)
         for l in range(len(self.top) - 1, -1, -1):
             w, b, act = self.top[l]
