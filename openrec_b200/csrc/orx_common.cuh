@@ -69,6 +69,10 @@ struct orx_ctx {
   int32_t* bucket_cursor;  // owner-bucket scratch
   cudaStream_t side_stream;  // orx_xchg_step: index build overlapped with the gradient exchange
   cudaEvent_t side_ev[2];
+  // ORX_HOST_COPY_STREAM=1 (experimental): the *_host entry points upload the next batch's ids on a copy stream
+  cudaStream_t copy_stream;
+  cudaEvent_t copy_done[2], stage_free[2];
+  int stage_free_valid[2];
   uint32_t epoch;          // hash epoch of the last step
 };
 

@@ -155,6 +155,13 @@ extern "C" int orx_destroy(orx_handle_t h) {
   cudaFree(h->counters);
   cudaFree(h->partials);
   cudaFree(h->bucket_cursor);
+  if (h->copy_stream) {
+    cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(h->copy_done[i]);
+      cudaEventDestroy(h->stage_free[i]);
+    }
+  }
   if (h->side_stream) {
     cudaStreamDestroy(h->side_stream);
     cudaEventDestroy(h->side_ev[0]);

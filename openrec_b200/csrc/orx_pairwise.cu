@@ -1164,12 +1164,45 @@ extern "C" int orx_pairwise_step_host(orx_handle_t h, int32_t kind, const orx_ta
   if (rc) return rc;
   const uint32_t f = (h->stage_flip++) & 1u;
   int32_t* ids = h->ids_stage[f];
-  ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-  ORX_CUDA(cudaMemcpyAsync(ids + B, pid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-  ORX_CUDA(cudaMemcpyAsync(ids + 2 * (int64_t)B, nid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+  static int use_copy_stream = -1;
+  if (use_copy_stream < 0) {
+    const char* e = getenv("ORX_HOST_COPY_STREAM");
+    use_copy_stream = (e && atoi(e)) ? 1 : 0;
+  }
+  if (use_copy_stream) {
+    // experimental: the upload of this batch runs on a copy stream, i.e. under the previous step's kernels when the
+    // caller enqueues ahead.  ids_stage[f] was last read by the step two calls ago: wait for that step first.
+    if (!h->copy_stream) {
+      ORX_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        ORX_CUDA(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
+        ORX_CUDA(cudaEventCreateWithFlags(&h->stage_free[i], cudaEventDisableTiming));
+        h->stage_free_valid[i] = 0;
+      }
+    }
+    cudaStream_t cs = h->copy_stream;
+    if (h->stage_free_valid[f]) ORX_CUDA(cudaStreamWaitEvent(cs, h->stage_free[f], 0));
+    if (pid_host == uid_host + B && nid_host == pid_host + B) {   // one contiguous (uid | pid | nid) host block
+      ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * 3 * (size_t)B, cudaMemcpyHostToDevice, cs));
+    } else {
+      ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
+      ORX_CUDA(cudaMemcpyAsync(ids + B, pid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
+      ORX_CUDA(cudaMemcpyAsync(ids + 2 * (int64_t)B, nid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
+    }
+    ORX_CUDA(cudaEventRecord(h->copy_done[f], cs));
+    ORX_CUDA(cudaStreamWaitEvent(st, h->copy_done[f], 0));
+  } else {
+    ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+    ORX_CUDA(cudaMemcpyAsync(ids + B, pid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+    ORX_CUDA(cudaMemcpyAsync(ids + 2 * (int64_t)B, nid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
+  }
   rc = pairwise_step_impl(h, kind, user, item, item_bias, ids, ids + B, ids + 2 * (int64_t)B, B, margin, c_loss, c_l2,
                           opt, h->out_stage[f], st);
   if (rc) return rc;
+  if (use_copy_stream) {
+    ORX_CUDA(cudaEventRecord(h->stage_free[f], st));
+    h->stage_free_valid[f] = 1;
+  }
   ORX_CUDA(cudaMemcpyAsync(out4_host, h->out_stage[f], sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
   return ORX_OK;
 }
