@@ -1,8 +1,8 @@
-"""openrec.tf2.modules surface (reference: openrec/tf2/modules/__init__.py:1-5)."""
-from .latent_factor import LatentFactor
-from .pairwise_log_loss import PairwiseLogLoss
-from .pointwise_mse_loss import PointwiseMSELoss
-from .multi_layer_perceptron import MLP
-from .second_order_feature_interaction import SecondOrderFeatureInteraction
+"""The five building blocks the tf2 recommenders are composed of (the names ``openrec.tf2.modules`` exports)."""
+from importlib import import_module
 
-__all__ = ["LatentFactor", "PairwiseLogLoss", "PointwiseMSELoss", "MLP", "SecondOrderFeatureInteraction"]
+_HOME = {"LatentFactor": "latent_factor", "PairwiseLogLoss": "pairwise_log_loss", "PointwiseMSELoss": "pointwise_mse_loss",
+         "MLP": "multi_layer_perceptron", "SecondOrderFeatureInteraction": "second_order_feature_interaction"}
+for _cls, _module in _HOME.items():
+    globals()[_cls] = getattr(import_module(f"{__name__}.{_module}"), _cls)
+__all__ = sorted(_HOME)

@@ -30,7 +30,7 @@ def _take(gen, n):
 
 def test_pairwise_stream_bit_exact(g):
     ds = _DataStore(raw_data=_raw(g), total_users=int(g["U"]), total_items=int(g["I"]), seed=123)
-    got = _take(D._pairwise_generator(ds), len(g["pairwise"]))
+    got = _take(D._Streams.pairwise(ds), len(g["pairwise"]))
     assert np.array_equal(got, g["pairwise"])          # same records, same negatives, same order
     pos = {}
     for u, i in zip(g["raw_user"], g["raw_item"]):
@@ -44,16 +44,16 @@ def test_pairwise_stream_bit_exact(g):
 
 def test_pointwise_streams_bit_exact(g):
     ds = _DataStore(raw_data=_raw(g), total_users=int(g["U"]), total_items=int(g["I"]), seed=5)
-    assert np.array_equal(_take(D._stratified_pointwise_generator(ds, 0.3), len(g["stratified"])), g["stratified"])
+    assert np.array_equal(_take(D._Streams.stratified(ds, 0.3), len(g["stratified"])), g["stratified"])
     ds = _DataStore(raw_data=_raw(g), total_users=int(g["U"]), total_items=int(g["I"]), seed=9)
-    assert np.array_equal(_take(D._per_pos_stratified_pointwise_generator(ds, 0.2), len(g["per_pos"])), g["per_pos"])
+    assert np.array_equal(_take(D._Streams.per_positive(ds, 0.2), len(g["per_pos"])), g["per_pos"])
 
 
 def test_evaluation_generator(g):
     raw = _raw(g)
     tr = Dataset(raw_data=raw[:200], total_users=int(g["U"]), total_items=int(g["I"]), seed=1)
     va = _DataStore(raw_data=raw[200:], total_users=int(g["U"]), total_items=int(g["I"]), seed=1)
-    ev = list(D._evaluation_generator(va, [tr]))
+    ev = list(D._Streams.evaluation(va, [tr]))
     assert np.array_equal(np.array([e["user_id"] for e in ev], dtype=np.int32), g["eval_user"])
     assert np.array_equal(np.stack([e["pos_mask"] for e in ev]), g["eval_pos"])
     assert np.array_equal(np.stack([e["excl_mask"] for e in ev]), g["eval_excl"])
