@@ -50,6 +50,7 @@ struct orx_ctx {
   // index workspace (sized for cap_B lookups per table side)
   int64_t cap_B;  // largest batch the workspace is sized for
   OrxHash hu, hi;
+  OrxHash hu_b, hi_b;  // second index set (ORX_OVERLAP_INDEX=1, experimental): lazily allocated, counters + 4
   int32_t* counters;  // [8]: 0 staged_u, 1 staged_i, 2 ticket, 3 bad ids, 4.. spare
   // staged-row gradient buffers
   float *gu, *gi, *gb, *gw;
@@ -277,6 +278,7 @@ struct TailArgs {
   int D;
   OrxOptDev opt;
   OrxHash hu, hi;
+  OrxHash hu_b, hi_b;  // second index set (ORX_OVERLAP_INDEX=1, experimental): lazily allocated, counters + 4
   float *gu, *gi, *gb;
   const float* partials;
   int n_partials;
@@ -301,6 +303,10 @@ int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t ro
                           const float* gstage, const OrxOptDev& o, cudaStream_t st);
 int orx_ensure_partials(orx_ctx* c, int need, cudaStream_t st);
 int orx_launch_reduce_partials(const float* partials, int n, float loss_scale, float* out4, cudaStream_t st);
+int orx_ensure_second_index(orx_ctx* c);
+int orx_launch_index_build_on(orx_ctx* c, OrxHash& hu, OrxHash& hi, int32_t* counters, const int32_t* a, int64_t rows_a,
+                              int32_t na, const int32_t* b0, const int32_t* b1, int64_t rows_b, int32_t nb, int mode,
+                              cudaStream_t st);
 int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
                            const int32_t* b1, int64_t rows_b, int32_t nb, int mode /* orx_hash_insert mode: 0 | 1 | 3 */,
                            cudaStream_t st);

@@ -37,6 +37,8 @@ static void free_hash(OrxHash& t) {
 static void free_workspace(orx_ctx* c) {
   free_hash(c->hu);
   free_hash(c->hi);
+  free_hash(c->hu_b);
+  free_hash(c->hi_b);
   cudaFree(c->gu);
   cudaFree(c->gi);
   cudaFree(c->gb);
@@ -96,6 +98,16 @@ int orx_ensure_workspace(orx_ctx* c, int64_t B, int32_t dim, bool /*full_staging
   c->cap_B = nb;
   c->g_dim = nd;
   c->epoch = 0;  // fresh (zeroed) tables: epochs restart at 1
+  return ORX_OK;
+}
+
+// second index set (same capacity as the first), used by the experimental index/step overlap of the *_host entry
+int orx_ensure_second_index(orx_ctx* c) {
+  if (c->hu_b.slots) return ORX_OK;
+  int rc;
+  if ((rc = alloc_hash(c->hu_b, c->cap_B, c->counters + 4)) != ORX_OK) return rc;
+  if ((rc = alloc_hash(c->hi_b, 2 * c->cap_B, c->counters + 5)) != ORX_OK) return rc;
+  ORX_CUDA(cudaMemset(c->counters + 4, 0, sizeof(int32_t) * 4));
   return ORX_OK;
 }
 

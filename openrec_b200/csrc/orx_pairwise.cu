@@ -74,11 +74,19 @@ int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride,
 
 int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
                            const int32_t* b1, int64_t rows_b, int32_t nb, int mode, cudaStream_t st) {
+  return orx_launch_index_build_on(c, c->hu, c->hi, c->counters, a, rows_a, na, b0, b1, rows_b, nb, mode, st);
+}
+
+// index build into an explicit (hash pair, counter block): the context's first set, or the second one of the
+// experimental index / step overlap.  Epochs come from the one context counter, so each set sees increasing values.
+int orx_launch_index_build_on(orx_ctx* c, OrxHash& hu, OrxHash& hi, int32_t* counters, const int32_t* a, int64_t rows_a,
+                              int32_t na, const int32_t* b0, const int32_t* b1, int64_t rows_b, int32_t nb, int mode,
+                              cudaStream_t st) {
   const int total = na + (b1 ? 2 * nb : nb);
   if (total <= 0) return ORX_OK;
-  orx_new_epoch(c);
-  k_index_build<<<(total + 255) / 256, 256, 0, st>>>(c->hu, c->hi, a, rows_a, na, b0, b1, rows_b, nb, mode,
-                                                    c->counters + 3);
+  c->epoch++;
+  hu.epoch = hi.epoch = c->epoch;
+  k_index_build<<<(total + 255) / 256, 256, 0, st>>>(hu, hi, a, rows_a, na, b0, b1, rows_b, nb, mode, counters + 3);
   ORX_LAUNCH_CHECK();
   return ORX_OK;
 }
@@ -1066,10 +1074,14 @@ static bool pair_fused_enabled() {
   return v != 0;
 }
 
+// index_stream != nullptr (experimental, LA variants only): the index is built into the context's SECOND hash set on
+// that stream (behind whatever the caller queued there, e.g. the id upload), `st` waits for it, and the previous step --
+// which uses the first set -- may still be running on `st` meanwhile.  `set` alternates per call.
 static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, const orx_table_t* item,
                               const orx_table_t* bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
                               int B, float margin, float c_loss, float c_l2, const orx_opt_t* opt, float* out4,
-                              cudaStream_t st) {
+                              cudaStream_t st, int set = 0, cudaStream_t index_stream = nullptr,
+                              cudaEvent_t index_done = nullptr) {
   ORX_REQUIRE(kind == ORX_PAIR_BPR || kind == ORX_PAIR_UCML, "unknown pairwise kind");
   ORX_REQUIRE(opt != nullptr && out4 != nullptr, "null opt/out");
   ORX_REQUIRE(opt->kind >= ORX_OPT_SGD && opt->kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
@@ -1107,10 +1119,26 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
   }
   // experimental "last arriver applies" variants (D = 128, not Keras-dense Adam): reference-counted index, no tail
   const bool la = D == 128 && !dense && opt->kind != ORX_OPT_ADAM_LAZY && (pair_variant() == 7 || pair_variant() == 8);
-  pa.out4 = la ? out4 : nullptr; pa.counters = c->counters; pa.loss_scale = (kind == ORX_PAIR_BPR) ? pa.inv_B : 1.0f;
-  if ((rc = orx_launch_index_build(c, uid, user->rows, B, pid, nid, item->rows, B, la ? 3 : (dense ? 1 : 0), st))) return rc;
+  const bool second = la && set == 1;
+  if (second && (rc = orx_ensure_second_index(c))) return rc;
+  OrxHash& HU = second ? c->hu_b : c->hu;
+  OrxHash& HI = second ? c->hi_b : c->hi;
+  int32_t* ctr = second ? c->counters + 4 : c->counters;
+  pa.out4 = la ? out4 : nullptr; pa.counters = ctr; pa.loss_scale = (kind == ORX_PAIR_BPR) ? pa.inv_B : 1.0f;
+  cudaStream_t ist = (la && index_stream) ? index_stream : st;
+  if (index_stream && !la) {   // no overlap without the LA variants: just order `st` behind the caller's id upload
+    ORX_CUDA(cudaEventRecord(index_done, index_stream));
+    ORX_CUDA(cudaStreamWaitEvent(st, index_done, 0));
+  }
+  if ((rc = orx_launch_index_build_on(c, HU, HI, ctr, uid, user->rows, B, pid, nid, item->rows, B,
+                                      la ? 3 : (dense ? 1 : 0), ist)))
+    return rc;
+  if (index_stream && la) {    // upload + index ran on index_stream: `st` (the step kernel) waits for both
+    ORX_CUDA(cudaEventRecord(index_done, index_stream));
+    ORX_CUDA(cudaStreamWaitEvent(st, index_done, 0));
+  }
   orx_prof_mark(c, 1, st);
-  pa.hu = c->hu; pa.hi = c->hi;
+  pa.hu = HU; pa.hi = HI;
   int n_partials = 0;
   rc = (kind == ORX_PAIR_BPR) ? launch_pair_step_kind<ORX_PAIR_BPR>(pa, opt->kind, st, &n_partials)
                               : launch_pair_step_kind<ORX_PAIR_UCML>(pa, opt->kind, st, &n_partials);
@@ -1188,6 +1216,22 @@ extern "C" int orx_pairwise_step_host(orx_handle_t h, int32_t kind, const orx_ta
       ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
       ORX_CUDA(cudaMemcpyAsync(ids + B, pid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
       ORX_CUDA(cudaMemcpyAsync(ids + 2 * (int64_t)B, nid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
+    }
+    static int overlap_index = -1;
+    if (overlap_index < 0) {
+      const char* e = getenv("ORX_OVERLAP_INDEX");
+      overlap_index = (e && atoi(e)) ? 1 : 0;
+    }
+    if (overlap_index) {
+      // experimental: the index build follows the upload on the copy stream into hash set f, so with the LA variants
+      // (no tail) it runs beside the previous step's k_pair_step, which uses the other set
+      rc = pairwise_step_impl(h, kind, user, item, item_bias, ids, ids + B, ids + 2 * (int64_t)B, B, margin, c_loss,
+                              c_l2, opt, h->out_stage[f], st, (int)f, cs, h->copy_done[f]);
+      if (rc) return rc;
+      ORX_CUDA(cudaEventRecord(h->stage_free[f], st));
+      h->stage_free_valid[f] = 1;
+      ORX_CUDA(cudaMemcpyAsync(out4_host, h->out_stage[f], sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
+      return ORX_OK;
     }
     ORX_CUDA(cudaEventRecord(h->copy_done[f], cs));
     ORX_CUDA(cudaStreamWaitEvent(st, h->copy_done[f], 0));
