@@ -365,7 +365,9 @@ def bench_single(args, eng, dev, barrier):
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_TRIPLET * B, "kernel_ms": step_ms,
                 "phase_ms_per_step": {"index_build": phase_ms[0] / max(n_prof, 1), "pair_step": step_ms,
                                       "tail": phase_ms[2] / max(n_prof, 1)},
-                "kernel_share_of_step": phase_ms[1] / max(sum(phase_ms), 1e-9)}
+                "kernel_share_of_step": phase_ms[1] / max(sum(phase_ms), 1e-9),
+                "timing": f"CUDA events around the three launches of every 8th step of the timed region ({n_prof} steps), "
+                          "on the stream the kernels run on (orx_profile_*)"}
     result = {"seconds": seconds, "e2e_seconds": e2e_seconds, "clocks": clocks.stop(), "launches": 3 * K,
               "roofline": roofline,
               "e2e_api": "openrec.tf2.recommenders.BPR + tf.GradientTape + tf.keras.optimizers.Adagrad (shim); "

@@ -66,6 +66,7 @@ struct orx_ctx {
   uint32_t stage_flip;
   // measurement hook (orx_profile_*)
   int prof_on, prof_n, prof_cap;
+  int prof_step;  // steps seen since orx_profile_enable: every 8th one carries the phase events
   cudaEvent_t* prof_ev;  // [prof_cap*4]
   int32_t* bucket_cursor;  // owner-bucket scratch
   cudaStream_t side_stream;  // orx_xchg_step: index build overlapped with the gradient exchange
@@ -84,11 +85,19 @@ static inline void orx_new_epoch(orx_ctx* c) {
 }
 
 // record phase boundary k (0..3) of the current step on `st` when profiling is enabled
+// Only every 8th step is instrumented: four timing-event records per step sit between the kernels of the step that is
+// being timed, and the un-instrumented loops of bench.py ran up to 10 % faster than the instrumented one (r1w: UCML
+// 612 M/s without events vs BPR 555 M/s with them, same kernel time under ncu).
+static inline bool orx_prof_sampled(const orx_ctx* c) {
+  return c->prof_on && (c->prof_step & 7) == 0 && c->prof_n < c->prof_cap;
+}
 static inline void orx_prof_mark(orx_ctx* c, int k, cudaStream_t st) {
-  if (c->prof_on && c->prof_n < c->prof_cap) cudaEventRecord(c->prof_ev[c->prof_n * 4 + k], st);
+  if (orx_prof_sampled(c)) cudaEventRecord(c->prof_ev[c->prof_n * 4 + k], st);
 }
 static inline void orx_prof_next(orx_ctx* c) {
-  if (c->prof_on && c->prof_n < c->prof_cap) c->prof_n++;
+  if (!c->prof_on) return;
+  if (orx_prof_sampled(c)) c->prof_n++;
+  c->prof_step++;
 }
 
 int orx_ensure_workspace(orx_ctx* c, int64_t B, int32_t dim, bool full_staging);

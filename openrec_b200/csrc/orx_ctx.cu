@@ -197,6 +197,7 @@ extern "C" int orx_profile_enable(orx_handle_t h, int32_t on) {
   }
   h->prof_on = on ? 1 : 0;
   h->prof_n = 0;
+  h->prof_step = 0;
   return ORX_OK;
 }
 
