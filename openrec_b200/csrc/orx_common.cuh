@@ -86,8 +86,8 @@ static inline void orx_new_epoch(orx_ctx* c) {
 
 // record phase boundary k (0..3) of the current step on `st` when profiling is enabled
 // Only every 8th step is instrumented: four timing-event records per step sit between the kernels of the step that is
-// being timed, and the un-instrumented loops of bench.py ran up to 10 % faster than the instrumented one (r1w: UCML
-// 612 M/s without events vs BPR 555 M/s with them, same kernel time under ncu).
+// being timed.  Suspected cost (not yet isolated): bench.py's un-instrumented UCML loop ran at 612 M/s against 555 M/s
+// for the instrumented BPR loop in r1w although both step kernels take 71 us under ncu.
 static inline bool orx_prof_sampled(const orx_ctx* c) {
   return c->prof_on && (c->prof_step & 7) == 0 && c->prof_n < c->prof_cap;
 }
