@@ -77,6 +77,8 @@ ORX_API int orx_destroy(orx_handle_t h);
 ORX_API int orx_device_count(int* n_out_host);
 /* Blocks the host until `stream` has drained (cudaStreamSynchronize). */
 ORX_API int orx_stream_synchronize(orx_handle_t h, orx_stream_t stream);
+/* Test hook: place the handle's batch-index epoch counter (31 bits; the wrap path empties the hash tables). */
+ORX_API int orx_debug_set_epoch(orx_handle_t h, uint32_t epoch);
 
 /* Measurement hook (bench.py's roofline): while enabled, every *_step call records CUDA events on its
  * launch stream around its kernels -- [0] batch index build, [1] the fused gather-score-update kernel,
@@ -116,6 +118,16 @@ ORX_API int orx_pairwise_step_host(orx_handle_t h, int32_t kind, const orx_table
                            const orx_table_t* item_bias, const int32_t* uid_host, const int32_t* pid_host,
                            const int32_t* nid_host, int32_t B, float margin, float c_loss, float c_l2,
                            const orx_opt_t* opt_host, float* out4_host, orx_stream_t s);
+/* Pipelining hint for device-resident ids: build the batch index (the dedup hash of the step) of (uid, pid, nid) NOW, on
+ * the handle's side stream, so that it runs beside whatever the step stream is doing (typically the previous step).
+ * ids_ready = 1: the id buffers are already complete (pre-staged batches); 0: they are complete once the work queued so
+ * far on ids_stream has run (e.g. a sampler kernel).  The next orx_pairwise_step called with exactly these pointers, B and
+ * optimizer kind waits for this index instead of building its own.  One outstanding prefetch; an unconsumed one is
+ * dropped.  The caller must not modify the id buffers until that step has run.  orx_pairwise_step_host pipelines the
+ * same way internally (upload + index of batch t under the kernels of batch t-1). */
+ORX_API int orx_pairwise_prefetch(orx_handle_t h, const orx_table_t* user, const orx_table_t* item, const int32_t* uid,
+                                  const int32_t* pid, const int32_t* nid, int32_t B, int32_t opt_kind, int32_t ids_ready,
+                                  orx_stream_t ids_stream);
 /* Forward only: (loss, l2_loss) -> out4[0..1]  (model(u,p,n) without a tape). */
 ORX_API int orx_pairwise_fwd(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
                      const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
@@ -183,67 +195,39 @@ ORX_API int orx_pairwise_grad_rows(orx_handle_t h, int32_t kind, const float* ro
                                    float margin, float c_loss, float c_l2, float inv_B, float* d_rows, float* out4,
                                    orx_stream_t s);
 
-/* ---- one-sided (peer-memory) sharded step over NVLink: no NCCL in the data path (openrec_b200/sharded_peer.py) ----
- * orx_peer_alloc/open/close/free: cudaMalloc + CUDA IPC handle (64 bytes) so every rank can map every other rank's
- *   shard and inbox.
- * orx_peer_t: device arrays (one entry per rank) of the mapped pointers.
- * orx_peer_pairwise_push: bucket positions of this rank's 3B lookups, per-owner counts published to the owners,
- *   then ONE kernel that gathers u/p/n rows from the owners with peer loads, scores, and pushes gradient rows +
- *   combined local row ids into the owners' inboxes with peer stores.  pos_scratch: int32[3B].
- * orx_peer_apply: the owner deduplicates all ranks' lookups found in its inbox and applies the optimizer once per
- *   unique row.  The caller places a cross-rank barrier before push (shards final) and between push and apply. */
+/* ---- row-sharded BPR / UCML step over the GPUs of one box, "home-routed" (openrec_b200/csrc/orx_shard.cu,
+ * openrec_b200/sharded.py).  The reference is single-device: this is the scale-out of the same synchronous step
+ * (tf2_examples/bpr_citeulike.py:33-39) and replaces the NCCL all-to-alls named in SURVEY 8(e) with peer STORES into
+ * IPC-mapped mailboxes.  Row r of the user / item tables lives on rank r % world at local row r / world; a triplet is
+ * computed on the rank that owns its user row.
+ * orx_peer_alloc/open/close/free: cudaMalloc + CUDA IPC handle (64 bytes) so every rank can map every peer's mailboxes.
+ * orx_shard_t: capacities + DEVICE arrays of `world` peer pointers, one per mailbox:
+ *   tripbox int32[world][3][batch_cap]  triplets routed to me, per source rank        idbox int32[world][req_cap]
+ *   got float[got_rows][dim], gotb float[got_rows]   item rows + biases for my triplets (got_rows = 2*home_cap+32*world)
+ *   gin float[gin_cap][dim], ginb float[gin_cap]     gradient rows + bias gradients for rows I own
+ *   meta int32[world][16]  per-peer counts / offsets / loss partials      flags int32[4*64+1] phase epochs + sticky error
+ * orx_shard_sizes: element counts (4-byte words) of the eight mailboxes, in the order above.
+ * orx_shard_step: the whole step in ONE call: seven launches on `s`, cross-rank ordering by flag words in peer memory
+ *   (no barrier launches, no collective, nothing returns to the host).  user/item/item_bias are this rank's LOCAL shards.
+ *   epoch: strictly increasing per step, starting at 1.  phase_lo..phase_hi (0..6) selects a sub-range of the launches so
+ *   that several virtual ranks can be stepped phase by phase on one device (the 1-GPU loopback test).
+ *   out4 = { loss, l2_loss (GLOBAL batch, identical on every rank), skipped triplets of this rank, staged rows }.
+ *   The sticky error word flags[4*64] is 0 or: 1 a peer never arrived within timeout_ms, 2 more triplets routed to this
+ *   home than home_cap, 3 / 4 request / gradient inbox too small.  SGD, Adagrad and row-sparse Adam. */
 typedef struct {
-  int32_t world, rank, dim, _pad;
-  int64_t total_users, total_items, cap;      /* cap: inbox capacity per source rank, >= 3*B */
-  void *emb, *bias, *inbox_emb, *inbox_bias, *inbox_ids, *inbox_cnt;   /* DEVICE arrays of `world` pointers */
-} orx_peer_t;
+  int32_t world, rank, dim, batch_cap, home_cap, req_cap, gin_cap, timeout_ms;
+  void *tripbox, *idbox, *got, *gotb, *gin, *ginb, *meta, *flags;   /* DEVICE arrays of `world` pointers */
+} orx_shard_t;
 ORX_API int orx_peer_alloc(orx_handle_t h, int64_t bytes, void** dev_ptr_out, uint8_t* handle_out64);
 ORX_API int orx_peer_open(orx_handle_t h, const uint8_t* handle64, void** dev_ptr_out);
 ORX_API int orx_peer_close(orx_handle_t h, void* dev_ptr);
 ORX_API int orx_peer_free(orx_handle_t h, void* dev_ptr);
-ORX_API int orx_peer_pairwise_push(orx_handle_t h, int32_t kind, const void* peer_host /* orx_peer_t* */,
-                                   const int32_t* uid, const int32_t* pid, const int32_t* nid, int32_t B,
-                                   int32_t* pos_scratch, float margin, float c_loss, float c_l2, float inv_B,
-                                   float* out4, orx_stream_t s);
-ORX_API int orx_peer_apply(orx_handle_t h, const orx_table_t* emb, const orx_table_t* bias, const int32_t* inbox_ids,
-                           const float* inbox_emb, const float* inbox_bias, const int32_t* inbox_cnt, int32_t world,
-                           int64_t cap, const orx_opt_t* opt_host, orx_stream_t s);
-
-/* ---- mailbox exchange of the row-sharded step: peer STORES into small IPC-mapped mailboxes, no NCCL in the data
- * path and no count on the host (openrec_b200/csrc/orx_xchg.cu, openrec_b200/sharded.py MailboxShardedPairwise).
- * Replaces the four collectives of the NCCL form of SURVEY 8(e).  orx_xchg_t: DEVICE arrays of `world` peer pointers:
- *   idbox int32[world][cap]   ids requested from me, per source rank      meta int32[world][8] per-peer counters + loss
- *   got   float[cap][width]   rows for my lookups, in my owner-sorted order
- *   gin   float[gin_rows][width] gradient rows for rows I own              flags int32[world+1] barrier epochs + error
- * Call order per step: orx_owner_bucket_combined, orx_xchg_push_ids, barrier, orx_xchg_gather_push, barrier,
- * orx_xchg_grad_push, barrier, orx_sparse_apply_devn(req, my gin, *n_dev).  orx_xchg_barrier is one such barrier
- * (epoch strictly increasing; a peer that never arrives within timeout_ms leaves flags[world] = 1 instead of a hang). */
-typedef struct {
-  int32_t world, rank, width, cap;
-  void *idbox, *meta, *got, *gin, *flags;
-} orx_xchg_t;
-ORX_API int orx_xchg_push_ids(orx_handle_t h, const void* xchg_host /* orx_xchg_t* */, const int32_t* counts,
-                              const int32_t* send_local, int32_t n, orx_stream_t s);
-ORX_API int orx_xchg_gather_push(orx_handle_t h, const void* xchg_host, const float* table, int64_t rows,
-                                 int32_t gin_rows, int32_t* req, int32_t* n_dev, int32_t* n_bad, orx_stream_t s);
-ORX_API int orx_xchg_grad_push(orx_handle_t h, int32_t kind, const void* xchg_host, const int32_t* counts,
-                               const int32_t* slot, int32_t B, int32_t dim, float margin, float c_loss, float c_l2,
-                               float inv_B, float* out4, orx_stream_t s);
-ORX_API int orx_xchg_barrier(orx_handle_t h, const void* xchg_host, int32_t epoch, int32_t timeout_ms, orx_stream_t s);
-/* The whole step in ONE call: 9 launches + 3 flag barriers, nothing returns to the host; out4[0..1] is the GLOBAL
- * (loss, l2_loss) on every rank (partials ride the meta mailboxes, no collective).  work: int32[world + 1 +
- * ceil(3B/1024)*world]; slot: int32[3B]; req: int32[gin_rows]; gin_local: local address of this rank's own gin;
- * barriers use epochs epoch_base+1..+3. */
-ORX_API int orx_xchg_step(orx_handle_t h, int32_t kind, const void* xchg_host, const orx_table_t* tab,
-                          const int32_t* uid, const int32_t* pid, const int32_t* nid, int32_t B, int64_t total_users,
-                          int32_t dim, const float* gin_local, int32_t gin_rows, int32_t* work, int32_t* slot,
-                          int32_t* req, float margin, float c_loss, float c_l2, float inv_B, const orx_opt_t* opt_host,
-                          int32_t epoch_base, int32_t timeout_ms, float* out4, orx_stream_t s);
-/* orx_sparse_apply with the pair count read from the device (*n_dev <= n_max); value rows have stride value_ld. */
-ORX_API int orx_sparse_apply_devn(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
-                                  int64_t value_ld, int32_t n_max, const int32_t* n_dev, const orx_opt_t* opt_host,
-                                  orx_stream_t s);
-
+ORX_API int orx_shard_sizes(const orx_shard_t* x_host, int64_t* n8_host);
+ORX_API int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x_host, const orx_table_t* user,
+                           const orx_table_t* item, const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid,
+                           const int32_t* nid, int32_t B, int64_t total_users, int64_t total_items, float margin,
+                           float c_loss, float c_l2, float inv_B, const orx_opt_t* opt_host, int32_t epoch,
+                           int32_t phase_lo, int32_t phase_hi, float* out4, orx_stream_t s);
 /* ---- dense variables (GMF w, MLP kernels/biases): Keras dense apply ---------------------- */
 ORX_API int orx_dense_apply(orx_handle_t h, float* var, float* s0, float* s1, const float* grad, int64_t n,
                     const orx_opt_t* opt_host, orx_stream_t s);

@@ -28,22 +28,17 @@ class OrxTable(C.Structure):
                 ("dim", C.c_int32)]
 
 
-class OrxPeer(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("dim", C.c_int32), ("_pad", C.c_int32),
-                ("total_users", C.c_int64), ("total_items", C.c_int64), ("cap", C.c_int64),
-                ("emb", C.c_void_p), ("bias", C.c_void_p), ("inbox_emb", C.c_void_p), ("inbox_bias", C.c_void_p),
-                ("inbox_ids", C.c_void_p), ("inbox_cnt", C.c_void_p)]
-
-
-class OrxXchg(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("width", C.c_int32), ("cap", C.c_int32),
-                ("idbox", C.c_void_p), ("meta", C.c_void_p), ("got", C.c_void_p), ("gin", C.c_void_p),
-                ("flags", C.c_void_p)]
+class OrxShard(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("dim", C.c_int32), ("batch_cap", C.c_int32),
+                ("home_cap", C.c_int32), ("req_cap", C.c_int32), ("gin_cap", C.c_int32), ("timeout_ms", C.c_int32),
+                ("tripbox", C.c_void_p), ("idbox", C.c_void_p), ("got", C.c_void_p), ("gotb", C.c_void_p),
+                ("gin", C.c_void_p), ("ginb", C.c_void_p), ("meta", C.c_void_p), ("flags", C.c_void_p)]
 
 
 _vp, _i32, _i64, _f, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 _T = C.POINTER(OrxTable)
 _O = C.POINTER(OrxOpt)
+_S = C.POINTER(OrxShard)
 
 # name -> argtypes (restype is int unless noted); mirrors include/orx.h one to one
 SIGNATURES = {
@@ -53,6 +48,7 @@ SIGNATURES = {
     "orx_destroy": [_vp],
     "orx_device_count": [C.POINTER(C.c_int)],
     "orx_stream_synchronize": [_vp, _vp],
+    "orx_debug_set_epoch": [_vp, C.c_uint32],
     "orx_profile_enable": [_vp, _i32],
     "orx_profile_read": [_vp, C.POINTER(C.c_float), C.POINTER(_i32)],
     "orx_fill_uniform": [_vp, _vp, _i64, _f, _f, _u64, _vp],
@@ -60,6 +56,7 @@ SIGNATURES = {
     "orx_censor": [_vp, _vp, _i64, _i32, _vp, _i32, _f, _vp],
     "orx_pairwise_step": [_vp, _i32, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _f, _O, _vp, _vp],
     "orx_pairwise_step_host": [_vp, _i32, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _f, _O, _vp, _vp],
+    "orx_pairwise_prefetch": [_vp, _T, _T, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "orx_pairwise_fwd": [_vp, _i32, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _vp, _vp],
     "orx_pairwise_grad": [_vp, _i32, _T, _T, _T, _vp, _vp, _vp, _i32, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "orx_pairwise_grad_slots": [_vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _f, _f, _f, _f, _vp, _vp, _vp,
@@ -77,15 +74,9 @@ SIGNATURES = {
     "orx_peer_open": [_vp, C.c_char_p, C.POINTER(_vp)],
     "orx_peer_close": [_vp, _vp],
     "orx_peer_free": [_vp, _vp],
-    "orx_peer_pairwise_push": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _f, _f, _f, _f, _vp, _vp],
-    "orx_peer_apply": [_vp, _T, _T, _vp, _vp, _vp, _vp, _i32, _i64, _O, _vp],
-    "orx_xchg_push_ids": [_vp, _vp, _vp, _vp, _i32, _vp],
-    "orx_xchg_gather_push": [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp],
-    "orx_xchg_grad_push": [_vp, _i32, _vp, _vp, _vp, _i32, _i32, _f, _f, _f, _f, _vp, _vp],
-    "orx_xchg_barrier": [_vp, _vp, _i32, _i32, _vp],
-    "orx_xchg_step": [_vp, _i32, _vp, _T, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _f, _f, _f, _f, _O,
-                      _i32, _i32, _vp, _vp],
-    "orx_sparse_apply_devn": [_vp, _T, _vp, _vp, _i64, _i32, _vp, _O, _vp],
+    "orx_shard_sizes": [_S, C.POINTER(_i64)],
+    "orx_shard_step": [_vp, _i32, _S, _T, _T, _T, _vp, _vp, _vp, _i32, _i64, _i64, _f, _f, _f, _f, _O, _i32, _i32, _i32,
+                       _vp, _vp],
     "orx_owner_bucket_combined": [_vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
     "orx_pairwise_grad_rows": [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _f, _f, _f, _f, _vp, _vp, _vp],
     "orx_owner_bucket": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],

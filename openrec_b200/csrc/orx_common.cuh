@@ -38,7 +38,6 @@ struct OrxHash {
   int32_t* didx;              // [cap]  compact staging index of a staged row
   int32_t* did;               // [cap_rows] row id of staging index d
   int32_t* counter;           // number of staged rows
-  unsigned long long* cnt;    // [cap]  (epoch << 32 | references) of a duplicated row -- "last arriver applies" variant only
   uint32_t mask;
   int32_t shift;  // 32 - log2(cap)
   uint32_t epoch;  // current epoch, >= 1
@@ -49,9 +48,9 @@ struct orx_ctx {
   int num_sms;
   // index workspace (sized for cap_B lookups per table side)
   int64_t cap_B;  // largest batch the workspace is sized for
-  OrxHash hu, hi;
-  OrxHash hu_b, hi_b;  // second index set (ORX_OVERLAP_INDEX=1, experimental): lazily allocated, counters + 4
-  int32_t* counters;  // [8]: 0 staged_u, 1 staged_i, 2 ticket, 3 bad ids, 4.. spare
+  OrxHash hu, hi;      // index set 0: everything that builds its index on the caller's stream
+  OrxHash pf_u[2], pf_i[2];  // index sets 1, 2: pairwise batches indexed ahead on the side stream (orx_pairwise.cu)
+  int32_t* counters;  // [16]: per index set k at 4k: staged_u, staged_i, ticket, bad ids; 12.. spare
   // staged-row gradient buffers
   float *gu, *gi, *gb, *gw;
   int64_t g_rows_u, g_rows_i;
@@ -69,20 +68,22 @@ struct orx_ctx {
   int prof_step;  // steps seen since orx_profile_enable: every 8th one carries the phase events
   cudaEvent_t* prof_ev;  // [prof_cap*4]
   int32_t* bucket_cursor;  // owner-bucket scratch
-  cudaStream_t side_stream;  // orx_xchg_step: index build overlapped with the gradient exchange
+  cudaStream_t side_stream;  // id upload + index build of the NEXT pairwise batch, beside the running step
   cudaEvent_t side_ev[2];
-  // ORX_HOST_COPY_STREAM=1 (experimental): the *_host entry points upload the next batch's ids on a copy stream
-  cudaStream_t copy_stream;
-  cudaEvent_t copy_done[2], stage_free[2];
-  int stage_free_valid[2];
-  uint32_t epoch;          // hash epoch of the last step
+  cudaEvent_t pf_done[2], pf_free[2], stage_free[2];   // prefetched index k built / handed back; id staging f free
+  int pf_free_valid[2], stage_free_valid[2];
+  int pf_valid, pf_set, pf_next, pf_B, pf_mode;        // the one outstanding prefetched index and what it was built for
+  const int32_t *pf_uid, *pf_pid, *pf_nid;
+  int64_t pf_rows_u, pf_rows_i;
+  uint32_t epoch;          // hash epoch of the last step, in [1, 2^31)
+  void* shard_ws;          // orx_shard.cu: local scratch of the row-sharded step (orx_shard_ws*)
 };
 
-// start a new hash epoch (call once per step before the index build)
-static inline void orx_new_epoch(orx_ctx* c) {
-  c->epoch++;
-  c->hu.epoch = c->hi.epoch = c->epoch;
-}
+// Start a new hash epoch (once per step, before the index build; `st` = the stream the step runs on).
+// A slot word holds 31 epoch bits: epochs live in [1, 2^31) and on wrap every table is zeroed on `st`, so a stale
+// slot can never alias the current epoch (about 65 h of back-to-back steps between wraps).
+int orx_next_epoch(orx_ctx* c, cudaStream_t st);
+void orx_shard_ws_release(orx_ctx* c);
 
 // record phase boundary k (0..3) of the current step on `st` when profiling is enabled
 // Only every 8th step is instrumented: four timing-event records per step sit between the kernels of the step that is
@@ -124,8 +125,7 @@ __device__ __forceinline__ unsigned long long orx_slot_word(uint32_t epoch, int3
 }
 
 // Insert one id.  mode 0: rows get a staging index when they are seen the SECOND time (duplicates only);
-// mode 1: on the FIRST occurrence (ADAM_DENSE stages every row); mode 2: never (pure dedup, censor);
-// mode 3: as mode 0, and every repeat is counted in cnt[slot] (total references of a duplicated row).
+// mode 1: on the FIRST occurrence (ADAM_DENSE stages every row); mode 2: never (pure dedup, censor).
 // Returns 0 if this call was the first occurrence of the id in this epoch, else 1.
 __device__ __forceinline__ uint32_t orx_hash_insert(const OrxHash& t, int32_t id, int mode) {
   const unsigned long long mine = orx_slot_word(t.epoch, id);
@@ -145,21 +145,9 @@ __device__ __forceinline__ uint32_t orx_hash_insert(const OrxHash& t, int32_t id
       w = old;                              // somebody else claimed it meanwhile (same epoch by construction)
     }
     if ((w & ~ORX_DUP_BIT) == mine) {
-      if (mode == 3) {   // reference count of a duplicated row: the first repeat sets (epoch, 2), later ones add 1
-        const unsigned long long fresh = ((unsigned long long)t.epoch << 32) | 2ull;
-        while (true) {
-          const unsigned long long c = __ldcg(t.cnt + h);
-          if ((uint32_t)(c >> 32) != t.epoch) {
-            if (atomicCAS(t.cnt + h, c, fresh) == c) break;
-          } else {
-            atomicAdd(t.cnt + h, 1ull);
-            break;
-          }
-        }
-      }
       if (!(w & ORX_DUP_BIT)) {
         const unsigned long long old = atomicOr(t.slots + h, ORX_DUP_BIT);
-        if ((mode == 0 || mode == 3) && !(old & ORX_DUP_BIT)) {   // this call made the row "shared": give it a staging slot
+        if (mode == 0 && !(old & ORX_DUP_BIT)) {   // this call made the row "shared": give it a staging slot
           const int d = atomicAdd(t.counter, 1);
           t.didx[h] = d;
           t.did[d] = id;
@@ -184,26 +172,6 @@ __device__ __forceinline__ uint32_t orx_hash_find(const OrxHash& t, int32_t id, 
     }
     if ((uint32_t)(w >> 33) != t.epoch) {
       *d = -1;
-      return 0u;
-    }
-    h = (h + 1) & t.mask;
-  }
-}
-
-// orx_hash_find that also returns the slot index (for cnt[slot])
-__device__ __forceinline__ uint32_t orx_hash_find_slot(const OrxHash& t, int32_t id, int32_t* d, int32_t* slot) {
-  const unsigned long long mine = orx_slot_word(t.epoch, id);
-  uint32_t h = orx_hash32((uint32_t)id, t.shift);
-  while (true) {
-    const unsigned long long w = __ldg(t.slots + h);
-    if ((w & ~ORX_DUP_BIT) == mine) {
-      *d = __ldg(t.didx + h);
-      *slot = (int32_t)h;
-      return (w & ORX_DUP_BIT) ? 2u : 1u;
-    }
-    if ((uint32_t)(w >> 33) != t.epoch) {
-      *d = -1;
-      *slot = -1;
       return 0u;
     }
     h = (h + 1) & t.mask;
@@ -287,7 +255,6 @@ struct TailArgs {
   int D;
   OrxOptDev opt;
   OrxHash hu, hi;
-  OrxHash hu_b, hi_b;  // second index set (ORX_OVERLAP_INDEX=1, experimental): lazily allocated, counters + 4
   float *gu, *gi, *gb;
   const float* partials;
   int n_partials;
@@ -300,22 +267,13 @@ struct TailArgs {
 };
 
 OrxOptDev orx_opt_to_dev(const orx_opt_t* o);
-int orx_sparse_apply_prebuilt(orx_ctx* h, const orx_table_t* tab, const int32_t* ids, const float* values, int64_t value_ld,
-                              int32_t n_max, const int32_t* n_dev, const orx_opt_t* opt, cudaStream_t st);
 int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride, int64_t rows, int32_t n,
                                    const int32_t* n_dev, bool stage_all, cudaStream_t st);
 int orx_launch_tail(orx_ctx* c, const TailArgs& ta, int opt_kind, cudaStream_t st);
-struct PairArgs;
-int orx_launch_pair_fused(orx_ctx* c, int kind, int opt_kind, PairArgs& pa, float loss_scale, float* out4,
-                          cudaStream_t st);
 int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t rows, int D, const OrxHash& h,
                           const float* gstage, const OrxOptDev& o, cudaStream_t st);
 int orx_ensure_partials(orx_ctx* c, int need, cudaStream_t st);
 int orx_launch_reduce_partials(const float* partials, int n, float loss_scale, float* out4, cudaStream_t st);
-int orx_ensure_second_index(orx_ctx* c);
-int orx_launch_index_build_on(orx_ctx* c, OrxHash& hu, OrxHash& hi, int32_t* counters, const int32_t* a, int64_t rows_a,
-                              int32_t na, const int32_t* b0, const int32_t* b1, int64_t rows_b, int32_t nb, int mode,
-                              cudaStream_t st);
 int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
-                           const int32_t* b1, int64_t rows_b, int32_t nb, int mode /* orx_hash_insert mode: 0 | 1 | 3 */,
+                           const int32_t* b1, int64_t rows_b, int32_t nb, int mode /* orx_hash_insert mode: 0 | 1 */,
                            cudaStream_t st);

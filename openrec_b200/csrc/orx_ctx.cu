@@ -27,8 +27,6 @@ static void free_hash(OrxHash& t) {
   cudaFree(t.slots);
   cudaFree(t.didx);
   cudaFree(t.did);
-  cudaFree(t.cnt);
-  t.cnt = nullptr;
   t.slots = nullptr;
   t.didx = nullptr;
   t.did = nullptr;
@@ -37,8 +35,10 @@ static void free_hash(OrxHash& t) {
 static void free_workspace(orx_ctx* c) {
   free_hash(c->hu);
   free_hash(c->hi);
-  free_hash(c->hu_b);
-  free_hash(c->hi_b);
+  for (int k = 0; k < 2; ++k) {
+    free_hash(c->pf_u[k]);
+    free_hash(c->pf_i[k]);
+  }
   cudaFree(c->gu);
   cudaFree(c->gi);
   cudaFree(c->gb);
@@ -66,9 +66,7 @@ static int alloc_hash(OrxHash& t, int64_t lookups, int32_t* counter) {
   ORX_CUDA(cudaMalloc(&t.slots, sizeof(unsigned long long) * cap));
   ORX_CUDA(cudaMalloc(&t.didx, sizeof(int32_t) * cap));
   ORX_CUDA(cudaMalloc(&t.did, sizeof(int32_t) * (lookups + 1)));
-  ORX_CUDA(cudaMalloc(&t.cnt, sizeof(unsigned long long) * cap));
   ORX_CUDA(cudaMemset(t.slots, 0, sizeof(unsigned long long) * cap));
-  ORX_CUDA(cudaMemset(t.cnt, 0, sizeof(unsigned long long) * cap));
   return ORX_OK;
 }
 
@@ -83,6 +81,12 @@ int orx_ensure_workspace(orx_ctx* c, int64_t B, int32_t dim, bool /*full_staging
   int rc;
   if ((rc = alloc_hash(c->hu, nb, c->counters + 0)) != ORX_OK) return rc;
   if ((rc = alloc_hash(c->hi, 2 * nb, c->counters + 1)) != ORX_OK) return rc;
+  for (int k = 0; k < 2; ++k) {
+    if ((rc = alloc_hash(c->pf_u[k], nb, c->counters + 4 * (1 + k))) != ORX_OK) return rc;
+    if ((rc = alloc_hash(c->pf_i[k], 2 * nb, c->counters + 4 * (1 + k) + 1)) != ORX_OK) return rc;
+  }
+  c->pf_valid = 0;
+  c->pf_free_valid[0] = c->pf_free_valid[1] = 0;
   c->g_rows_u = nb;
   c->g_rows_i = 2 * nb;
   size_t bu = sizeof(float) * (size_t)c->g_rows_u * nd, bi = sizeof(float) * (size_t)c->g_rows_i * nd;
@@ -94,20 +98,42 @@ int orx_ensure_workspace(orx_ctx* c, int64_t B, int32_t dim, bool /*full_staging
   ORX_CUDA(cudaMemset(c->gi, 0, bi));
   ORX_CUDA(cudaMemset(c->gb, 0, sizeof(float) * (size_t)c->g_rows_i));
   ORX_CUDA(cudaMemset(c->gw, 0, sizeof(float) * (size_t)nd));
-  ORX_CUDA(cudaMemset(c->counters, 0, sizeof(int32_t) * 8));
+  ORX_CUDA(cudaMemset(c->counters, 0, sizeof(int32_t) * 16));
+  // the memsets above ran on the legacy default stream; the caller's stream may be a non-blocking one
+  ORX_CUDA(cudaDeviceSynchronize());
   c->cap_B = nb;
   c->g_dim = nd;
   c->epoch = 0;  // fresh (zeroed) tables: epochs restart at 1
   return ORX_OK;
 }
 
-// second index set (same capacity as the first), used by the experimental index/step overlap of the *_host entry
-int orx_ensure_second_index(orx_ctx* c) {
-  if (c->hu_b.slots) return ORX_OK;
-  int rc;
-  if ((rc = alloc_hash(c->hu_b, c->cap_B, c->counters + 4)) != ORX_OK) return rc;
-  if ((rc = alloc_hash(c->hi_b, 2 * c->cap_B, c->counters + 5)) != ORX_OK) return rc;
-  ORX_CUDA(cudaMemset(c->counters + 4, 0, sizeof(int32_t) * 4));
+static int zero_hash(OrxHash& t) {
+  if (!t.slots) return ORX_OK;
+  ORX_CUDA(cudaMemset(t.slots, 0, sizeof(unsigned long long) * ((size_t)t.mask + 1)));
+  return ORX_OK;
+}
+
+int orx_next_epoch(orx_ctx* c, cudaStream_t /*st*/) {
+  c->epoch = (c->epoch + 1) & 0x7fffffffu;
+  if (c->epoch == 0) {
+    // 31-bit wrap (once per 2^31 index builds): a stale slot could alias the epochs to come, so every table is emptied.
+    // Index builds may be in flight on two streams: drain the device around the memsets.
+    ORX_CUDA(cudaDeviceSynchronize());
+    int rc;
+    if ((rc = zero_hash(c->hu)) || (rc = zero_hash(c->hi))) return rc;
+    for (int k = 0; k < 2; ++k)
+      if ((rc = zero_hash(c->pf_u[k])) || (rc = zero_hash(c->pf_i[k]))) return rc;
+    ORX_CUDA(cudaDeviceSynchronize());
+    c->epoch = 1;
+  }
+  c->hu.epoch = c->hi.epoch = c->epoch;
+  return ORX_OK;
+}
+
+// test hook: place the epoch counter (tests/test_gpu_kernels.py::test_epoch_wrap starts it just below 2^31)
+extern "C" int orx_debug_set_epoch(orx_handle_t h, uint32_t epoch) {
+  ORX_REQUIRE(h != nullptr && epoch < 0x80000000u, "null handle / epoch must be < 2^31");
+  h->epoch = epoch;
   return ORX_OK;
 }
 
@@ -142,7 +168,7 @@ extern "C" int orx_create(int device, orx_handle_t* out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->cap_partials = c->num_sms * 64;
-  if (cudaMalloc(&c->counters, sizeof(int32_t) * 8) != cudaSuccess ||
+  if (cudaMalloc(&c->counters, sizeof(int32_t) * 16) != cudaSuccess ||
       cudaMalloc(&c->partials, sizeof(float) * 2 * (size_t)c->cap_partials) != cudaSuccess ||
       cudaMalloc(&c->out_stage[0], sizeof(float) * 8) != cudaSuccess ||
       cudaMalloc(&c->out_stage[1], sizeof(float) * 8) != cudaSuccess) {
@@ -150,7 +176,7 @@ extern "C" int orx_create(int device, orx_handle_t* out) {
     delete c;
     return ORX_ERR_NOMEM;
   }
-  cudaMemset(c->counters, 0, sizeof(int32_t) * 8);
+  cudaMemset(c->counters, 0, sizeof(int32_t) * 16);
   *out = c;
   return ORX_OK;
 }
@@ -167,17 +193,15 @@ extern "C" int orx_destroy(orx_handle_t h) {
   cudaFree(h->counters);
   cudaFree(h->partials);
   cudaFree(h->bucket_cursor);
-  if (h->copy_stream) {
-    cudaStreamDestroy(h->copy_stream);
-    for (int i = 0; i < 2; ++i) {
-      cudaEventDestroy(h->copy_done[i]);
-      cudaEventDestroy(h->stage_free[i]);
-    }
-  }
+  orx_shard_ws_release(h);
   if (h->side_stream) {
     cudaStreamDestroy(h->side_stream);
-    cudaEventDestroy(h->side_ev[0]);
-    cudaEventDestroy(h->side_ev[1]);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(h->side_ev[i]);
+      cudaEventDestroy(h->pf_done[i]);
+      cudaEventDestroy(h->pf_free[i]);
+      cudaEventDestroy(h->stage_free[i]);
+    }
   }
   if (h->prof_ev) {
     for (int i = 0; i < h->prof_cap * 4; ++i) cudaEventDestroy(h->prof_ev[i]);

@@ -106,7 +106,7 @@ extern "C" int orx_censor(orx_handle_t h, float* tab, int64_t rows, int32_t dim,
   cudaStream_t st = (cudaStream_t)s;
   int rc = orx_ensure_workspace(h, n, h->g_dim > 0 ? h->g_dim : 1, false);
   if (rc) return rc;
-  orx_new_epoch(h);   // the dedup hash needs no clearing: a new epoch empties it
+  if ((rc = orx_next_epoch(h, st))) return rc;   // the dedup hash needs no clearing: a new epoch empties it
   k_censor<<<(n + 7) / 8, 256, 0, st>>>(tab, rows, dim, ids, n, min_norm, h->hu);
   ORX_LAUNCH_CHECK();
   return ORX_OK;

@@ -80,165 +80,11 @@ __device__ __forceinline__ void split_tf32(float v, float* hi, float* lo) {
   *lo = to_tf32(v - h);
 }
 
-// A tile source: TA=0 -> A[m*lda + k] (row-major [M,K]); TA=1 -> A[k*lda + m] ([K,M] row-major).
-// B tile source: TB=0 -> B[k*ldb + n] ([K,N] row-major); TB=1 -> B[n*ldb + k] ([N,K] row-major).
-// `rows` counts along M (A) or N (B); both tiles are staged as [128 rows][32 k] K-major.
-template <int T>  // T=0: source is [rows, K] row-major (k contiguous); T=1: source is [K, rows] row-major
-__device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t ld, int r0, int k0, int R, int K,
-                                           unsigned char* hi_tile, unsigned char* lo_tile) {
-  if (T == 0) {
-    // 128 rows x 8 float4 per row = 1024 float4; 128 threads -> 8 each; consecutive threads walk k (coalesced)
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int e = it * 128 + threadIdx.x;
-      const int r = e >> 3, kq = (e & 7) * 4;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (r0 + r < R) {
-        const float* p = src + (int64_t)(r0 + r) * ld + k0 + kq;
-        if (k0 + kq + 3 < K && ((((uintptr_t)p) & 15) == 0)) {
-          const float4 q = *reinterpret_cast<const float4*>(p);
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        } else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (k0 + kq + c < K) v[c] = p[c];
-        }
-      }
-      float4 h, l;
-      split_tf32(v[0], &h.x, &l.x); split_tf32(v[1], &h.y, &l.y); split_tf32(v[2], &h.z, &l.z); split_tf32(v[3], &h.w, &l.w);
-      const int off = tile_off(r, kq);
-      *reinterpret_cast<float4*>(hi_tile + off) = h;
-      *reinterpret_cast<float4*>(lo_tile + off) = l;
-    }
-  } else {
-    // source [K, rows]: consecutive threads walk rows (coalesced), 32 k x 128 rows = 4096 scalars, 32 per thread
-#pragma unroll 8
-    for (int it = 0; it < 32; ++it) {
-      const int k = it, r = threadIdx.x;
-      float v = 0.f;
-      if (k0 + k < K && r0 + r < R) v = src[(int64_t)(k0 + k) * ld + r0 + r];
-      float h, l;
-      split_tf32(v, &h, &l);
-      const int off = tile_off(r, k);
-      *reinterpret_cast<float*>(hi_tile + off) = h;
-      *reinterpret_cast<float*>(lo_tile + off) = l;
-    }
-  }
-}
-
 // The tensor core accumulates in fp32 with truncation; over hundreds of accumulations that bias grows linearly
 // with K (measured 3e-4 abs at K=1024).  So a TMEM accumulator only ever sums GROUP_KB k-blocks (64 K-elements,
 // 24 MMAs); it is then drained with tcgen05.ld into fp32 REGISTERS (round-to-nearest adds, one output row per
 // thread).  Two TMEM accumulators alternate, so the drain of group g-1 overlaps the MMAs of group g.
 constexpr int GROUP_KB = 2;
-
-template <int TA, int TB>
-__global__ void __launch_bounds__(128, 1) k_gemm_tc(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
-                                                    int64_t ldb, float* __restrict__ C, int64_t ldc, int M, int N, int K,
-                                                    const float* __restrict__ bias, int act) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ __align__(8) uint64_t mbar[NSTAGE];   // smem stage free again (its MMAs finished)
-  __shared__ __align__(8) uint64_t accbar[2];      // TMEM accumulator buffer complete (its group's MMAs finished)
-  __shared__ uint32_t tmem_base_s;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-
-  if (warp == 0) {   // TMEM: 2 x 128 fp32 accumulator columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(&mbar[s], 1);
-    mbar_init(&accbar[0], 1);
-    mbar_init(&accbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_base_s;
-
-  float acc[BN];   // this thread's output row (m0 + 32*warp + lane), fp32 accumulation across groups
-#pragma unroll
-  for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-
-  // drain TMEM accumulator `buf` (group number g) into the register accumulators
-  auto drain = [&](int g) {
-    const int buf = g & 1;
-    mbar_wait(&accbar[buf], (g >> 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + c0);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  };
-
-  const int nkb = (K + BK - 1) / BK;
-  const int ngroups = (nkb + GROUP_KB - 1) / GROUP_KB;
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % NSTAGE;
-    const int g = kb / GROUP_KB;                 // accumulation group and its TMEM buffer
-    const bool g_first = (kb % GROUP_KB) == 0, g_last = (kb % GROUP_KB) == GROUP_KB - 1 || kb == nkb - 1;
-    unsigned char* st = smem + (size_t)s * STAGE_BYTES;
-    if (kb >= NSTAGE) mbar_wait(&mbar[s], ((kb / NSTAGE) - 1) & 1);   // MMAs of block kb-NSTAGE are done with this stage
-    stage_tile<TA>(A, lda, m0, kb * BK, M, K, st, st + TILE_BYTES);
-    stage_tile<(TB == 1 ? 0 : 1)>(Bm, ldb, n0, kb * BK, N, K, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
-    // group g reuses the TMEM buffer of group g-2: every thread must have drained g-2 before its first MMA.
-    // (the drain of g-2 ran after group g-1's first block was issued, i.e. earlier in program order)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
-      const uint32_t d = tmem_d + (uint32_t)((g & 1) * BN);
-#pragma unroll
-      for (int ks = 0; ks < BK / 8; ++ks) {           // one MMA consumes K = 8 (two 16-byte core matrices = 256 B)
-        const uint32_t o = ks * 256;
-        mma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), (g_first && ks == 0) ? 0u : 1u);
-        mma_tf32(d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
-        mma_tf32(d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
-      }
-      umma_commit(&mbar[s]);                 // stage s may be overwritten once these MMAs are done
-      if (g_last) umma_commit(&accbar[g & 1]);   // ... and the group's accumulator is complete
-    }
-    // overlap: while group g's MMAs run, fold the previous group's accumulator into the registers
-    if (g_first && g >= 1) drain(g - 1);
-  }
-  drain(ngroups - 1);
-
-  // epilogue from registers: thread = one row
-  const int m = m0 + warp * 32 + lane;
-  if (m < M) {
-#pragma unroll
-    for (int j = 0; j < BN; ++j) {
-      const int n = n0 + j;
-      if (n < N) {
-        float x = acc[j] + (bias ? bias[n] : 0.f);
-        if (act == 1) x = fmaxf(x, 0.f);
-        else if (act == 2) x = orx_sigmoid(x);
-        C[(int64_t)m * ldc + n] = x;
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_d) : "memory");
-}
-
 
 // ---------------------------------------------------------------------------------------
 // Version 2 of the tile kernel (default): same tcgen05 / TMEM / descriptor code as k_gemm_tc above, different division
@@ -444,210 +290,6 @@ __global__ void __launch_bounds__(NT2, 1) k_gemm_tc2(const float* __restrict__ A
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_d) : "memory");
 }
 
-// ---------------------------------------------------------------------------------------
-// Version 3 (experimental, ORX_MLP_TC_V=3; not yet run on a GPU): the global loads become cp.async copies into a
-// 3-deep ring of RAW fp32 tiles in shared memory (no registers held, two k-blocks of latency cover), and the hi/lo split
-// reads the raw tile from shared memory.  v2 exposes most of the global latency of every k-block (its one register
-// stage is covered only by the MMA issue and the drain); here the k-block time should be convert + sync + MMA.
-//   shared memory: 3 x (A_raw 16 KB + B_raw 16 KB) + 2 x (A_hi, A_lo, B_hi, B_lo = 64 KB) = 224 KB.
-//   raw tile of a [rows, K] source: [128 rows][32 k]; of a [K, rows] source: [32 k][128 rows]  (as in global memory)
-// Needs 16-byte aligned rows (ld % 4 == 0, base % 16 == 0); other shapes fall back to v2.
-// ---------------------------------------------------------------------------------------
-constexpr int RAW_STAGES = 3;
-constexpr int RAW_BYTES = 2 * TILE_BYTES;     // A_raw + B_raw
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-
-// issue the copies of one raw tile (1024 16-byte chunks, 4 per thread); out-of-range parts are zero-filled
-template <int T>
-__device__ __forceinline__ void raw_copy(const float* __restrict__ src, int64_t ld, int r0, int k0, int R, int K, unsigned char* raw) {
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int e = it * NT2 + threadIdx.x;
-    if (T == 0) {          // chunk = row r, k0+kq .. +3
-      const int r = e >> 3, kq = (e & 7) * 4;
-      int valid = (r0 + r < R) ? (K - (k0 + kq)) : 0;
-      valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
-      const float* p = valid ? src + (int64_t)(r0 + r) * ld + k0 + kq : src;
-      cp_async16(raw + r * 128 + kq * 4, p, valid * 4);
-    } else {               // chunk = k, rows r0+4rq .. +3
-      const int k = e >> 5, rq = (e & 31) * 4;
-      int valid = (k0 + k < K) ? (R - (r0 + rq)) : 0;
-      valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
-      const float* p = valid ? src + (int64_t)(k0 + k) * ld + r0 + rq : src;
-      cp_async16(raw + k * 512 + rq * 4, p, valid * 4);
-    }
-  }
-}
-
-// raw tile -> hi / lo operand tiles in the K-major no-swizzle UMMA layout
-template <int T>
-__device__ __forceinline__ void raw_convert(const unsigned char* raw, unsigned char* hi_tile, unsigned char* lo_tile) {
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int e = it * NT2 + threadIdx.x;
-    float4 v;
-    int r, kq;
-    if (T == 0) {
-      r = e >> 3; kq = (e & 7) * 4;
-      v = *reinterpret_cast<const float4*>(raw + r * 128 + kq * 4);
-    } else {
-      r = e & 127; kq = (e >> 7) * 4;
-      const float* f = reinterpret_cast<const float*>(raw);
-      v = make_float4(f[(kq + 0) * 128 + r], f[(kq + 1) * 128 + r], f[(kq + 2) * 128 + r], f[(kq + 3) * 128 + r]);
-    }
-    float4 h, l;
-    split_tf32(v.x, &h.x, &l.x); split_tf32(v.y, &h.y, &l.y); split_tf32(v.z, &h.z, &l.z); split_tf32(v.w, &h.w, &l.w);
-    const int off = tile_off(r, kq);
-    *reinterpret_cast<float4*>(hi_tile + off) = h;
-    *reinterpret_cast<float4*>(lo_tile + off) = l;
-  }
-}
-
-template <int TA, int TB>
-__global__ void __launch_bounds__(NT2, 1) k_gemm_tc3(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bm,
-                                                     int64_t ldb, float* __restrict__ C, int64_t ldc, int M, int N, int K,
-                                                     const float* __restrict__ bias, int act, float* __restrict__ part) {
-  extern __shared__ __align__(1024) unsigned char smem[];   // [2 op stages | 3 raw stages]
-  __shared__ __align__(8) uint64_t mbar[NSTAGE];
-  __shared__ __align__(8) uint64_t accbar[2];
-  __shared__ uint32_t tmem_base_s;
-  unsigned char* raw_base = smem + (size_t)NSTAGE * STAGE_BYTES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  constexpr int HN = BN / 2;
-  const int chalf = (warp >> 2) * HN;
-  const int lane_base = (warp & 3) * 32;
-
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(&mbar[s], 1);
-    mbar_init(&accbar[0], 1);
-    mbar_init(&accbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_base_s;
-
-  float acc[HN];
-#pragma unroll
-  for (int j = 0; j < HN; ++j) acc[j] = 0.f;
-
-  auto drain = [&](int g) {
-    const int buf = g & 1;
-    mbar_wait(&accbar[buf], (g >> 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-    for (int c0 = 0; c0 < HN; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)lane_base << 16) + (uint32_t)(buf * BN + chalf + c0);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  };
-
-  const int nkb_all = (K + BK - 1) / BK;
-  const int per = (nkb_all + (int)gridDim.z - 1) / (int)gridDim.z;
-  const int kb_lo = blockIdx.z * per;
-  const int kb_hi = min(nkb_all, kb_lo + per);
-  const int nkb = max(0, kb_hi - kb_lo);
-  const int ngroups = (nkb + GROUP_KB - 1) / GROUP_KB;
-
-  auto issue_raw = [&](int kb) {     // always commits a group, so "all but the newest RAW_STAGES-1 groups" is uniform
-    if (kb < nkb) {
-      unsigned char* raw = raw_base + (size_t)(kb % RAW_STAGES) * RAW_BYTES;
-      const int k0 = (kb_lo + kb) * BK;
-      raw_copy<TA>(A, lda, m0, k0, M, K, raw);
-      raw_copy<(TB == 1 ? 0 : 1)>(Bm, ldb, n0, k0, N, K, raw + TILE_BYTES);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  for (int kb = 0; kb < RAW_STAGES - 1; ++kb) issue_raw(kb);
-
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % NSTAGE;
-    const int g = kb / GROUP_KB;
-    const bool g_first = (kb % GROUP_KB) == 0, g_last = (kb % GROUP_KB) == GROUP_KB - 1 || kb == nkb - 1;
-    unsigned char* st = smem + (size_t)s * STAGE_BYTES;
-    const unsigned char* raw = raw_base + (size_t)(kb % RAW_STAGES) * RAW_BYTES;
-    issue_raw(kb + RAW_STAGES - 1);   // its ring slot held block kb-1, which every thread converted before the last barrier
-    asm volatile("cp.async.wait_group %0;" ::"n"(RAW_STAGES - 1) : "memory");   // my copies of block kb have landed
-    __syncthreads();                                                            // ... and everybody else's
-    if (kb >= NSTAGE) mbar_wait(&mbar[s], ((kb / NSTAGE) - 1) & 1);   // the MMAs of block kb-NSTAGE are done with this stage
-    raw_convert<TA>(raw, st, st + TILE_BYTES);
-    raw_convert<(TB == 1 ? 0 : 1)>(raw + TILE_BYTES, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
-      const uint32_t d = tmem_d + (uint32_t)((g & 1) * BN);
-#pragma unroll
-      for (int ks = 0; ks < BK / 8; ++ks) {
-        const uint32_t o = ks * 256;
-        mma_tf32(d, make_desc(a_hi + o), make_desc(b_hi + o), (g_first && ks == 0) ? 0u : 1u);
-        mma_tf32(d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
-        mma_tf32(d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
-      }
-      umma_commit(&mbar[s]);
-      if (g_last) umma_commit(&accbar[g & 1]);
-    }
-    if (g_first && g >= 1) drain(g - 1);
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  if (ngroups > 0) drain(ngroups - 1);
-
-  __syncthreads();
-  float* tile = reinterpret_cast<float*>(smem);
-  {
-    const int r = lane_base + lane;
-#pragma unroll
-    for (int j = 0; j < HN; ++j) tile[r * (BN + 1) + chalf + j] = acc[j];
-  }
-  __syncthreads();
-  const bool split = gridDim.z > 1;
-  float* out = split ? part + (size_t)blockIdx.z * (size_t)M * (size_t)N : C;
-  const int64_t ldo = split ? (int64_t)N : ldc;
-  for (int r = warp; r < BM; r += NT2 / 32) {
-    const int m = m0 + r;
-    if (m >= M) break;
-#pragma unroll
-    for (int c = 0; c < BN; c += 32) {
-      const int n = n0 + c + lane;
-      if (n < N) {
-        float x = tile[r * (BN + 1) + c + lane];
-        if (!split) {
-          x += bias ? bias[n] : 0.f;
-          if (act == 1) x = fmaxf(x, 0.f);
-          else if (act == 2) x = orx_sigmoid(x);
-        }
-        out[(int64_t)m * ldo + n] = x;
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_d) : "memory");
-}
-
 // sum of split-K partials (deterministic: fixed order), + bias, activation
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int S, int M, int N, float* __restrict__ C,
                                                        int64_t ldc, const float* __restrict__ bias, int act) {
@@ -690,17 +332,11 @@ int orx_launch_splitk_reduce(const float* part, int S, int M, int N, float* C, i
 
 // C[M,N] = op(A) * op(B) (+bias, act) on tcgen05; same operand conventions as launch_gemm in orx_dlrm.cu.
 // Returns ORX_ERR_UNSUPPORTED for shapes that are better left to the SIMT kernel (tiny N or K).
-// ORX_MLP_TC_V=1 selects the first version of the tile kernel (k_gemm_tc), default is k_gemm_tc2.
 int orx_launch_gemm_tc(int TA, int TB, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc,
                        int M, int N, int K, const float* bias, int act, cudaStream_t st) {
   if (N < 16 || K < 8 || M < 64) return ORX_ERR_UNSUPPORTED;
-  static int version = -1;
-  if (version < 0) {
-    const char* e = getenv("ORX_MLP_TC_V");
-    version = (e && atoi(e) == 1) ? 1 : ((e && atoi(e) == 3) ? 3 : 2);
-  }
   const size_t smem = (size_t)NSTAGE * STAGE_BYTES + 1024;
-  if (version >= 2) {
+  {
     const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
     const int nkb = (K + BK - 1) / BK;
     int S = 1;
@@ -724,48 +360,13 @@ int orx_launch_gemm_tc(int TA, int TB, const float* A, int64_t lda, const float*
     }                                                                                                             \
     k_gemm_tc2<ta, tb><<<grid, NT2, smem, st>>>(A, lda, Bm, ldb, C, ldc, M, N, K, bias, act, part);                \
   }
-    // v3 (experimental): cp.async raw ring; needs 16-byte aligned operand rows
-    const bool v3 = version == 3 && (lda & 3) == 0 && (ldb & 3) == 0 && ((((uintptr_t)A) | ((uintptr_t)Bm)) & 15) == 0;
-    const size_t smem3 = (size_t)NSTAGE * STAGE_BYTES + (size_t)RAW_STAGES * RAW_BYTES;
-#define ORX_TC3(ta, tb)                                                                                            \
-  {                                                                                                                \
-    static bool done3 = false;                                                                                     \
-    if (!done3) {                                                                                                  \
-      ORX_CUDA(cudaFuncSetAttribute(k_gemm_tc3<ta, tb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
-      done3 = true;                                                                                                \
-    }                                                                                                              \
-    k_gemm_tc3<ta, tb><<<grid, NT2, smem3, st>>>(A, lda, Bm, ldb, C, ldc, M, N, K, bias, act, part);                \
-  }
-    if (v3) {
-      if (TA == 0 && TB == 0) ORX_TC3(0, 0)
-      else if (TA == 0 && TB == 1) ORX_TC3(0, 1)
-      else if (TA == 1 && TB == 0) ORX_TC3(1, 0)
-      else ORX_TC3(1, 1)
-    } else if (TA == 0 && TB == 0) ORX_TC2(0, 0)
+    if (TA == 0 && TB == 0) ORX_TC2(0, 0)
     else if (TA == 0 && TB == 1) ORX_TC2(0, 1)
     else if (TA == 1 && TB == 0) ORX_TC2(1, 0)
     else ORX_TC2(1, 1)
 #undef ORX_TC2
-#undef ORX_TC3
     ORX_LAUNCH_CHECK();
     if (S > 1) return orx_launch_splitk_reduce(part, S, M, N, C, ldc, bias, act, st);
     return ORX_OK;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-#define ORX_TC(ta, tb)                                                                                          \
-  {                                                                                                             \
-    static bool done = false;                                                                                   \
-    if (!done) {                                                                                                \
-      ORX_CUDA(cudaFuncSetAttribute(k_gemm_tc<ta, tb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      done = true;                                                                                              \
-    }                                                                                                           \
-    k_gemm_tc<ta, tb><<<grid, 128, smem, st>>>(A, lda, Bm, ldb, C, ldc, M, N, K, bias, act);                     \
-  }
-  if (TA == 0 && TB == 0) ORX_TC(0, 0)
-  else if (TA == 0 && TB == 1) ORX_TC(0, 1)
-  else if (TA == 1 && TB == 0) ORX_TC(1, 0)
-  else ORX_TC(1, 1)
-#undef ORX_TC
-  ORX_LAUNCH_CHECK();
-  return ORX_OK;
 }

@@ -16,10 +16,6 @@ struct PairArgs {
   float *gu, *gi, *gb;
   float* partials;
   float* g_out;
-  // "last arriver applies" variant only (k_pair_step<..., LA = true>): the step's own epilogue replaces the tail launch
-  float* out4;
-  int32_t* counters;
-  float loss_scale;
 };
 
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }

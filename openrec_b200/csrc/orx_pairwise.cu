@@ -27,18 +27,6 @@ __global__ void k_index_build(OrxHash hu, OrxHash hi, const int32_t* __restrict_
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = na + (b1 ? 2 * nb : nb);
   if (i >= total) return;
-  if (stage_all == 3) {
-    // reference-counting mode (pairwise only: na == nb, b1 != 0): a triplet with ANY id out of range is skipped as a
-    // whole by k_pair_step, so none of its ids may be counted -- the counts must equal the decrements
-    const int tq = i < na ? i : (i - na < nb ? i - na : i - na - nb);
-    const int32_t x = a[tq], y = b0[tq], z = b1[tq];
-    const bool ok = x >= 0 && (int64_t)x < rows_a && y >= 0 && (int64_t)y < rows_b && z >= 0 && (int64_t)z < rows_b;
-    const int32_t id = i < na ? x : (i - na < nb ? y : z);
-    const bool mine_ok = id >= 0 && (int64_t)id < (i < na ? rows_a : rows_b);
-    if (!mine_ok) atomicAdd(bad, 1);
-    if (ok) orx_hash_insert(i < na ? hu : hi, id, 3);
-    return;
-  }
   if (i < na) {
     const int32_t id = a[i];
     if (id >= 0 && (int64_t)id < rows_a) orx_hash_insert(hu, id, stage_all);
@@ -64,7 +52,8 @@ __global__ void k_index_build_strided(OrxHash hu, const int32_t* __restrict__ a,
 int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride, int64_t rows, int32_t n,
                                    const int32_t* n_dev, bool stage_all, cudaStream_t st) {
   if (n <= 0) return ORX_OK;
-  orx_new_epoch(c);
+  int rc = orx_next_epoch(c, st);
+  if (rc) return rc;
   int blocks = (n + 255) / 256;
   if (n_dev && blocks > c->num_sms * 8) blocks = c->num_sms * 8;
   k_index_build_strided<<<blocks, 256, 0, st>>>(c->hu, a, stride, rows, n, n_dev, stage_all ? 1 : 0, c->counters + 3);
@@ -74,19 +63,11 @@ int orx_launch_index_build_strided(orx_ctx* c, const int32_t* a, int64_t stride,
 
 int orx_launch_index_build(orx_ctx* c, const int32_t* a, int64_t rows_a, int32_t na, const int32_t* b0,
                            const int32_t* b1, int64_t rows_b, int32_t nb, int mode, cudaStream_t st) {
-  return orx_launch_index_build_on(c, c->hu, c->hi, c->counters, a, rows_a, na, b0, b1, rows_b, nb, mode, st);
-}
-
-// index build into an explicit (hash pair, counter block): the context's first set, or the second one of the
-// experimental index / step overlap.  Epochs come from the one context counter, so each set sees increasing values.
-int orx_launch_index_build_on(orx_ctx* c, OrxHash& hu, OrxHash& hi, int32_t* counters, const int32_t* a, int64_t rows_a,
-                              int32_t na, const int32_t* b0, const int32_t* b1, int64_t rows_b, int32_t nb, int mode,
-                              cudaStream_t st) {
   const int total = na + (b1 ? 2 * nb : nb);
   if (total <= 0) return ORX_OK;
-  c->epoch++;
-  hu.epoch = hi.epoch = c->epoch;
-  k_index_build<<<(total + 255) / 256, 256, 0, st>>>(hu, hi, a, rows_a, na, b0, b1, rows_b, nb, mode, counters + 3);
+  int rc = orx_next_epoch(c, st);
+  if (rc) return rc;
+  k_index_build<<<(total + 255) / 256, 256, 0, st>>>(c->hu, c->hi, a, rows_a, na, b0, b1, rows_b, nb, mode, c->counters + 3);
   ORX_LAUNCH_CHECK();
   return ORX_OK;
 }
@@ -100,7 +81,6 @@ struct TripRegs {
   float4 us0[K], ps0[K], ns0[K];  // dead arrays are eliminated when the optimizer has no such slot
   float4 us1[K], ps1[K], ns1[K];
   int fl, uu, pp, nn, du, dp, dn;
-  int su, sp, sn;  // hash slot of the row (reference counter), LA variant only
   float bp, bn;
 };
 
@@ -110,12 +90,7 @@ struct TripRegs {
 //   ids (coalesced, lanes < CH) -> variable rows of the first one/two triplet groups (they need only
 //   the ids) -> hash probes + bias loads (lanes < CH, overlap the row loads) -> slot rows of the first
 //   groups -> steady state: process one register buffer while the other's 128-bit loads are in flight.
-// LA ("last arriver applies", ORX_PAIR_VARIANT=7/8, experimental): shared rows carry a reference count built by
-// k_index_build (mode 3).  After a triplet has RED-added its gradient for a shared row it decrements the count; the
-// contributor that takes it to zero applies the optimizer to that row on the spot.  Every other reader's load of the
-// row precedes that reader's own decrement, so all gathers still see pre-step values, and the tail launch disappears
-// (loss reduction + counter reset move to a last-block-done epilogue).  DESIGN.md section 10.1.
-template <int KIND, int OPT, int D, int CH, int MINB, bool PIPE, bool LA = false>
+template <int KIND, int OPT, int D, int CH, int MINB, bool PIPE>
 __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
   constexpr int G = (D / 4 < 32) ? D / 4 : 32;  // lanes per triplet
   constexpr int K = D / (4 * G);                // float4 per lane per row
@@ -162,18 +137,10 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
 
   // ---- hash probes + item_bias (lanes < CH), overlapping the row loads above
   float bp = 0.f, bn = 0.f, bps0 = 0.f, bps1 = 0.f, bns0 = 0.f, bns1 = 0.f;
-  int hsu = -1, hsp = -1, hsn = -1;
   if (flags & 1) {
-    uint32_t cu, cp, cn;
-    if constexpr (LA) {
-      cu = orx_hash_find_slot(a.hu, u_id, &du, &hsu);
-      cp = orx_hash_find_slot(a.hi, p_id, &dp, &hsp);
-      cn = orx_hash_find_slot(a.hi, n_id, &dn, &hsn);
-    } else {
-      cu = orx_hash_find(a.hu, u_id, &du);
-      cp = orx_hash_find(a.hi, p_id, &dp);
-      cn = orx_hash_find(a.hi, n_id, &dn);
-    }
+    const uint32_t cu = orx_hash_find(a.hu, u_id, &du);
+    const uint32_t cp = orx_hash_find(a.hi, p_id, &dp);
+    const uint32_t cn = orx_hash_find(a.hi, n_id, &dn);
     bp = __ldcg(a.Bv + p_id);
     bn = __ldcg(a.Bv + n_id);
     if (!STAGE_ONLY) {
@@ -198,11 +165,6 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
     r.dn = __shfl_sync(ORX_FULL, dn, src);
     r.bp = __shfl_sync(ORX_FULL, bp, src);
     r.bn = __shfl_sync(ORX_FULL, bn, src);
-    if constexpr (LA) {
-      r.su = __shfl_sync(ORX_FULL, hsu, src);
-      r.sp = __shfl_sync(ORX_FULL, hsp, src);
-      r.sn = __shfl_sync(ORX_FULL, hsn, src);
-    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const int off = (k * G + gl) * 4;
@@ -282,59 +244,6 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
           orx_red4(a.gi + (int64_t)r.dn * D + off, gn);
         }
       }
-      if constexpr (LA && !STAGE_ONLY) {
-        const int shared = (~r.fl) & 14;   // rows of this triplet that went to the staging buffers
-        if (shared) {
-          // bias contributions of shared item rows must be in before the reference is given back
-          if (gl == 0) {
-            if (shared & 4) atomicAdd(a.gb + r.dp, gbias);
-            if (shared & 8) atomicAdd(a.gb + r.dn, -gbias);
-          }
-          __threadfence();                 // my REDs / atomics are visible before my decrements
-          int last = 0;
-          if (gl == 0) {
-            if ((shared & 2) && (uint32_t)atomicAdd(a.hu.cnt + r.su, ~0ull) == 1u) last |= 2;
-            if ((shared & 4) && (uint32_t)atomicAdd(a.hi.cnt + r.sp, ~0ull) == 1u) last |= 4;
-            if ((shared & 8) && (uint32_t)atomicAdd(a.hi.cnt + r.sn, ~0ull) == 1u) last |= 8;
-          }
-          last = __shfl_sync(ORX_FULL, last, grp * G);
-          if (last) {
-            __threadfence();               // every contributor's REDs happened before its decrement, hence before mine
-            auto apply_row = [&](float* W, float* P0, float* P1, float* stage, int id, int d, const float4* cur) {
-#pragma unroll
-              for (int k = 0; k < K; ++k) {
-                const int off = (k * G + gl) * 4;
-                const int64_t o = (int64_t)id * D + off;
-                float* sp_ = stage + (int64_t)d * D + off;
-                const float4 gs = __ldcg(reinterpret_cast<const float4*>(sp_));
-                float4 s0v = S0 ? __ldcg(reinterpret_cast<const float4*>(P0 + o)) : z4;
-                float4 s1v = S1 ? __ldcg(reinterpret_cast<const float4*>(P1 + o)) : z4;
-                __stcg(reinterpret_cast<float4*>(W + o), orx_apply4<OPT>(cur[k], gs, s0v, s1v, a.opt));
-                if (S0) __stcg(reinterpret_cast<float4*>(P0 + o), s0v);
-                if (S1) __stcg(reinterpret_cast<float4*>(P1 + o), s1v);
-                __stcg(reinterpret_cast<float4*>(sp_), z4);
-              }
-            };
-            auto apply_bias = [&](int id, int d) {   // item rows only; one lane
-              const float gbv = __ldcg(a.gb + d);
-              float s0v = S0 ? __ldcg(a.Bs0 + id) : 0.f, s1v = S1 ? __ldcg(a.Bs1 + id) : 0.f;
-              __stcg(a.Bv + id, orx_apply<OPT>(__ldcg(a.Bv + id), gbv, s0v, s1v, a.opt));
-              if (S0) __stcg(a.Bs0 + id, s0v);
-              if (S1) __stcg(a.Bs1 + id, s1v);
-              __stcg(a.gb + d, 0.f);
-            };
-            if (last & 2) apply_row(a.U, a.Us0, a.Us1, a.gu, r.uu, r.du, r.u);
-            if (last & 4) {
-              apply_row(a.I, a.Is0, a.Is1, a.gi, r.pp, r.dp, r.p);
-              if (gl == 0) apply_bias(r.pp, r.dp);
-            }
-            if (last & 8) {
-              apply_row(a.I, a.Is0, a.Is1, a.gi, r.nn, r.dn, r.n);
-              if (gl == 0) apply_bias(r.nn, r.dn);
-            }
-          }
-        }
-      }
     }
   };
 
@@ -371,14 +280,14 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
       __stcg(a.Bv + p_id, orx_apply<OPT>(bp, g_own, bps0, bps1, a.opt));
       if (S0) __stcg(a.Bs0 + p_id, bps0);
       if (S1) __stcg(a.Bs1 + p_id, bps1);
-    } else if (!LA || STAGE_ONLY) {
+    } else {
       atomicAdd(a.gb + dp, g_own);
     }
     if (flags & 8) {
       __stcg(a.Bv + n_id, orx_apply<OPT>(bn, -g_own, bns0, bns1, a.opt));
       if (S0) __stcg(a.Bs0 + n_id, bns0);
       if (S1) __stcg(a.Bs1 + n_id, bns1);
-    } else if (!LA || STAGE_ONLY) {
+    } else {
       atomicAdd(a.gb + dn, -g_own);
     }
     if (a.g_out) a.g_out[t] = (KIND == ORX_PAIR_BPR) ? g_own : -g_own;
@@ -393,272 +302,6 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
   if (lane == 0) {
     sred[threadIdx.x >> 5][0] = loss_acc;
     sred[threadIdx.x >> 5][1] = l2_acc;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float l = 0.f, q = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      l += sred[w][0];
-      q += sred[w][1];
-    }
-    a.partials[2 * blockIdx.x] = l;
-    a.partials[2 * blockIdx.x + 1] = q;
-  }
-  if constexpr (LA) {
-    // last block done: deterministic (fixed order, double) reduction of the per-block partials, out4, counter reset
-    __shared__ bool is_last;
-    __shared__ double dred[2][256];
-    if (threadIdx.x == 0) {
-      __threadfence();
-      is_last = (atomicAdd(a.counters + 2, 1) == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-      __threadfence();
-      double l = 0.0, q = 0.0;
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
-        l += (double)__ldcg(a.partials + 2 * i);
-        q += (double)__ldcg(a.partials + 2 * i + 1);
-      }
-      dred[0][threadIdx.x] = l;
-      dred[1][threadIdx.x] = q;
-      __syncthreads();
-      for (int sft = 128; sft > 0; sft >>= 1) {
-        if (threadIdx.x < sft) {
-          dred[0][threadIdx.x] += dred[0][threadIdx.x + sft];
-          dred[1][threadIdx.x] += dred[1][threadIdx.x + sft];
-        }
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) {
-        a.out4[0] = (float)(dred[0][0] * (double)a.loss_scale);
-        a.out4[1] = (float)(0.5 * dred[1][0]);
-        a.out4[2] = (float)a.counters[3];
-        a.out4[3] = (float)(a.counters[0] + a.counters[1]);
-        a.counters[0] = a.counters[1] = a.counters[2] = a.counters[3] = 0;
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// cp.async variant: the rows of the next STAGES triplet groups are in flight in a per-warp shared-memory
-// ring (LDGSTS.128, no registers held while in flight), so memory-level parallelism is set by STAGES x
-// resident warps instead of by the register file.  Each lane copies and later reads only ITS OWN 16 bytes of
-// every row, so no cross-lane synchronisation is needed: cp.async.wait_group orders a thread's own copies.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void orx_cp_async16(float4* smem_dst, const float* gsrc, bool pred) {
-  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int bytes = pred ? 16 : 0;   // src-size 0 => the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gsrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void orx_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void orx_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int KIND, int OPT, int D, int CH, int MINB, int STAGES>
-__global__ void __launch_bounds__(256, MINB) k_pair_step_async(const PairArgs a) {
-  constexpr int G = (D / 4 < 32) ? D / 4 : 32;
-  constexpr int K = D / (4 * G);
-  constexpr int TPW = 32 / G;
-  constexpr int NG = CH / TPW;  // triplet groups per warp
-  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
-  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
-  constexpr bool STAGE_ONLY = (OPT == ORX_OPT_ADAM_DENSE);
-  constexpr int NR = 3 + (S0 ? 3 : 0) + (S1 ? 3 : 0);  // rows per triplet in the ring
-  static_assert(CH % TPW == 0 && STAGES >= 1 && STAGES <= NG, "bad staging");
-  extern __shared__ float4 orx_ring[];
-
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int grp = lane / G, gl = lane % G;
-  const int t = warp * CH + lane;
-  float4* ring = orx_ring + (size_t)wib * STAGES * NR * K * 32 + lane;   // this lane's column of the warp's ring
-  auto slot = [&](int stage, int row, int k) -> float4* { return ring + ((stage * NR + row) * K + k) * 32; };
-
-  int u_id = 0, p_id = 0, n_id = 0, du = -1, dp = -1, dn = -1, flags = 0;
-  if (lane < CH && t < a.B) {
-    u_id = a.uid[t];
-    p_id = a.pid[t];
-    n_id = a.nid[t];
-    flags = (u_id >= 0 && u_id < a.rowsU && p_id >= 0 && p_id < a.rowsI && n_id >= 0 && n_id < a.rowsI) ? 1 : 0;
-  }
-
-  auto issue_var = [&](int g, int stage) {
-    const int src = g * TPW + grp;
-    const bool v = __shfl_sync(ORX_FULL, flags, src) & 1;
-    const int uu = __shfl_sync(ORX_FULL, u_id, src), pp = __shfl_sync(ORX_FULL, p_id, src),
-              nn = __shfl_sync(ORX_FULL, n_id, src);
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int off = (k * G + gl) * 4;
-      orx_cp_async16(slot(stage, 0, k), v ? a.U + (int64_t)uu * D + off : a.U, v);
-      orx_cp_async16(slot(stage, 1, k), v ? a.I + (int64_t)pp * D + off : a.I, v);
-      orx_cp_async16(slot(stage, 2, k), v ? a.I + (int64_t)nn * D + off : a.I, v);
-    }
-  };
-  auto issue_slots = [&](int g, int stage) {
-    if (!S0) return;
-    const int src = g * TPW + grp;
-    const int fl = __shfl_sync(ORX_FULL, flags, src);
-    const int uu = __shfl_sync(ORX_FULL, u_id, src), pp = __shfl_sync(ORX_FULL, p_id, src),
-              nn = __shfl_sync(ORX_FULL, n_id, src);
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int off = (k * G + gl) * 4;
-      orx_cp_async16(slot(stage, 3, k), (fl & 2) ? a.Us0 + (int64_t)uu * D + off : a.Us0, fl & 2);
-      orx_cp_async16(slot(stage, 4, k), (fl & 4) ? a.Is0 + (int64_t)pp * D + off : a.Is0, fl & 4);
-      orx_cp_async16(slot(stage, 5, k), (fl & 8) ? a.Is0 + (int64_t)nn * D + off : a.Is0, fl & 8);
-      if (S1) {
-        orx_cp_async16(slot(stage, 6, k), (fl & 2) ? a.Us1 + (int64_t)uu * D + off : a.Us1, fl & 2);
-        orx_cp_async16(slot(stage, 7, k), (fl & 4) ? a.Is1 + (int64_t)pp * D + off : a.Is1, fl & 4);
-        orx_cp_async16(slot(stage, 8, k), (fl & 8) ? a.Is1 + (int64_t)nn * D + off : a.Is1, fl & 8);
-      }
-    }
-  };
-
-  // variable rows of the first STAGES groups go out before the hash probes
-#pragma unroll
-  for (int g = 0; g < STAGES; ++g) issue_var(g, g);
-
-  float bp = 0.f, bn = 0.f, bps0 = 0.f, bps1 = 0.f, bns0 = 0.f, bns1 = 0.f;
-  if (flags & 1) {
-    const uint32_t cu = orx_hash_find(a.hu, u_id, &du);
-    const uint32_t cp = orx_hash_find(a.hi, p_id, &dp);
-    const uint32_t cn = orx_hash_find(a.hi, n_id, &dn);
-    bp = __ldcg(a.Bv + p_id);
-    bn = __ldcg(a.Bv + n_id);
-    if (!STAGE_ONLY) {
-      flags |= (cu == 1u ? 2 : 0) | (cp == 1u ? 4 : 0) | (cn == 1u ? 8 : 0);
-      if (S0) {
-        if (flags & 4) bps0 = __ldcg(a.Bs0 + p_id);
-        if (flags & 8) bns0 = __ldcg(a.Bs0 + n_id);
-      }
-      if (S1) {
-        if (flags & 4) bps1 = __ldcg(a.Bs1 + p_id);
-        if (flags & 8) bns1 = __ldcg(a.Bs1 + n_id);
-      }
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < STAGES; ++g) {
-    issue_slots(g, g);
-    orx_cp_commit();   // group g = slots(g) (+ every var row issued so far for g == 0)
-  }
-
-  float loss_acc = 0.f, l2_acc = 0.f, g_own = 0.f;
-#pragma unroll 1
-  for (int g = 0; g < NG; ++g) {
-    const int stage = g % STAGES;
-    orx_cp_wait<STAGES - 1>();
-    const int src = g * TPW + grp;
-    const int fl = __shfl_sync(ORX_FULL, flags, src);
-    const int uu = __shfl_sync(ORX_FULL, u_id, src), pp = __shfl_sync(ORX_FULL, p_id, src),
-              nn = __shfl_sync(ORX_FULL, n_id, src);
-    const int duj = __shfl_sync(ORX_FULL, du, src), dpj = __shfl_sync(ORX_FULL, dp, src),
-              dnj = __shfl_sync(ORX_FULL, dn, src);
-    const float bpj = __shfl_sync(ORX_FULL, bp, src), bnj = __shfl_sync(ORX_FULL, bn, src);
-    float4 u[K], p[K], n[K];
-    float s1 = 0.f, s2 = 0.f, sq = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      u[k] = *slot(stage, 0, k);
-      p[k] = *slot(stage, 1, k);
-      n[k] = *slot(stage, 2, k);
-      if (KIND == ORX_PAIR_BPR) {
-        s1 += dot4(u[k], p[k]);
-        s2 += dot4(u[k], n[k]);
-      } else {
-        s1 += sqd4(u[k], p[k]);
-        s2 += sqd4(u[k], n[k]);
-      }
-      sq += dot4(u[k], u[k]) + dot4(p[k], p[k]) + dot4(n[k], n[k]);
-    }
-    l2_acc += sq;
-    s1 = orx_group_sum<G>(s1);
-    s2 = orx_group_sum<G>(s2);
-    float lt, gsc;
-    pair_score<KIND>(s1, s2, bpj, bnj, a, &lt, &gsc);
-    const bool v = fl & 1;
-    if (!v) { lt = 0.f; gsc = 0.f; }
-    if (gl == 0) loss_acc += lt;
-    const float gbias = (KIND == ORX_PAIR_BPR) ? gsc : -gsc;
-#pragma unroll
-    for (int q = 0; q < TPW; ++q) {
-      const float val = __shfl_sync(ORX_FULL, gbias, q * G);
-      if (lane == g * TPW + q) g_own = val;
-    }
-    if (v) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const int off = (k * G + gl) * 4;
-        float4 gu, gp, gn;
-        pair_row_grads<KIND>(gsc, a.c_l2, u[k], p[k], n[k], &gu, &gp, &gn);
-        float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0;
-        if (!STAGE_ONLY && (fl & 2)) {
-          const int64_t o = (int64_t)uu * D + off;
-          float4 a0 = S0 ? *slot(stage, 3, k) : z0, a1 = S1 ? *slot(stage, 6, k) : z1;
-          __stcg(reinterpret_cast<float4*>(a.U + o), orx_apply4<OPT>(u[k], gu, a0, a1, a.opt));
-          if (S0) __stcg(reinterpret_cast<float4*>(a.Us0 + o), a0);
-          if (S1) __stcg(reinterpret_cast<float4*>(a.Us1 + o), a1);
-        } else {
-          orx_red4(a.gu + (int64_t)duj * D + off, gu);
-        }
-        if (!STAGE_ONLY && (fl & 4)) {
-          const int64_t o = (int64_t)pp * D + off;
-          float4 a0 = S0 ? *slot(stage, 4, k) : z0, a1 = S1 ? *slot(stage, 7, k) : z1;
-          __stcg(reinterpret_cast<float4*>(a.I + o), orx_apply4<OPT>(p[k], gp, a0, a1, a.opt));
-          if (S0) __stcg(reinterpret_cast<float4*>(a.Is0 + o), a0);
-          if (S1) __stcg(reinterpret_cast<float4*>(a.Is1 + o), a1);
-        } else {
-          orx_red4(a.gi + (int64_t)dpj * D + off, gp);
-        }
-        if (!STAGE_ONLY && (fl & 8)) {
-          const int64_t o = (int64_t)nn * D + off;
-          float4 a0 = S0 ? *slot(stage, 5, k) : z0, a1 = S1 ? *slot(stage, 8, k) : z1;
-          __stcg(reinterpret_cast<float4*>(a.I + o), orx_apply4<OPT>(n[k], gn, a0, a1, a.opt));
-          if (S0) __stcg(reinterpret_cast<float4*>(a.Is0 + o), a0);
-          if (S1) __stcg(reinterpret_cast<float4*>(a.Is1 + o), a1);
-        } else {
-          orx_red4(a.gi + (int64_t)dnj * D + off, gn);
-        }
-      }
-    }
-    if (g + STAGES < NG) {   // refill the slot just consumed
-      issue_var(g + STAGES, stage);
-      issue_slots(g + STAGES, stage);
-    }
-    orx_cp_commit();         // one group per iteration (possibly empty) keeps wait_group<STAGES-1> exact
-  }
-
-  if (flags & 1) {
-    if (flags & 4) {
-      __stcg(a.Bv + p_id, orx_apply<OPT>(bp, g_own, bps0, bps1, a.opt));
-      if (S0) __stcg(a.Bs0 + p_id, bps0);
-      if (S1) __stcg(a.Bs1 + p_id, bps1);
-    } else {
-      atomicAdd(a.gb + dp, g_own);
-    }
-    if (flags & 8) {
-      __stcg(a.Bv + n_id, orx_apply<OPT>(bn, -g_own, bns0, bns1, a.opt));
-      if (S0) __stcg(a.Bs0 + n_id, bns0);
-      if (S1) __stcg(a.Bs1 + n_id, bns1);
-    } else {
-      atomicAdd(a.gb + dn, -g_own);
-    }
-    if (a.g_out) a.g_out[t] = (KIND == ORX_PAIR_BPR) ? g_own : -g_own;
-  } else if (a.g_out && lane < CH && t < a.B) {
-    a.g_out[t] = 0.f;
-  }
-
-  __shared__ float sred[8][2];
-  loss_acc = orx_group_sum<32>(loss_acc);
-  l2_acc = orx_group_sum<32>(l2_acc);
-  if (lane == 0) {
-    sred[wib][0] = loss_acc;
-    sred[wib][1] = l2_acc;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -976,21 +619,11 @@ int orx_launch_adam_sweep(orx_ctx* c, float* var, float* m, float* v, int64_t ro
 // ---------------------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------------------
-// Tuning variants of the D=128 kernel, selected with ORX_PAIR_VARIANT (A/B on the GPU):
-//   0: 2 CTAs/SM, register double-buffer             1: 3 CTAs/SM, double-buffer
-//   2 (default, fastest in profiles r1b/r1c): 4 CTAs/SM, single buffer   3: 3 CTAs/SM, single buffer
-//   4/5/6: cp.async shared-memory ring, (stages, CTAs/SM) = (4,2) / (3,3) / (2,4)
-static int pair_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ORX_PAIR_VARIANT");
-    v = e ? atoi(e) : 2;
-  }
-  return v;
-}
-
+// D = 128 runs 4 CTAs/SM with a single register buffer (64 registers): the fastest of the variants A/B-tested in
+// profiles r1b/r1c/r2a (2-3 CTAs/SM with a register double-buffer, a cp.async shared-memory ring, and a
+// "last arriver applies" form without the tail launch were all slower and are gone).
 template <int KIND, int OPT>
-static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaStream_t st, int* n_partials) {
+static int launch_pair_step_kind_opt(const PairArgs& pa, cudaStream_t st, int* n_partials) {
   const int B = pa.B;
   constexpr bool LAZY = (OPT == ORX_OPT_ADAM_LAZY);  // 9 rows per triplet: no register double-buffer
   auto go = [&](auto kern, int ch) {
@@ -999,37 +632,12 @@ static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaS
     *n_partials = blocks;
     kern<<<blocks, 256, 0, st>>>(pa);
   };
-  auto go_async = [&](auto kern, int ch, int stages) {
-    constexpr int NRr = 3 + ((OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY) ? 3 : 0) + (LAZY ? 3 : 0);
-    const size_t smem = (size_t)8 * stages * NRr * (pa.D / 128 > 0 ? pa.D / 128 : 1) * 512;
-    const int nw = (B + ch - 1) / ch;
-    const int blocks = (nw + 7) / 8;
-    *n_partials = blocks;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<blocks, 256, smem, st>>>(pa);
-  };
-  (void)n_warps_hint;
   switch (pa.D) {
     case 32: go(k_pair_step<KIND, OPT, 32, 8, 2, !LAZY>, 8); break;
     case 64: go(k_pair_step<KIND, OPT, 64, 8, 2, !LAZY>, 8); break;
     case 128:
-      switch (LAZY ? 3 : pair_variant()) {
-        case 0: go(k_pair_step<KIND, OPT, 128, 8, 2, !LAZY>, 8); break;
-        case 1: go(k_pair_step<KIND, OPT, 128, 8, 3, !LAZY>, 8); break;
-        case 3: go(k_pair_step<KIND, OPT, 128, 8, 3, false>, 8); break;
-        case 4: go_async(k_pair_step_async<KIND, OPT, 128, 8, 2, 4>, 8, 4); break;
-        case 5: go_async(k_pair_step_async<KIND, OPT, 128, 8, 3, 3>, 8, 3); break;
-        case 6: go_async(k_pair_step_async<KIND, OPT, 128, 8, 4, 2>, 8, 2); break;
-        case 7:   // last arriver applies (pa.out4 is set only when the caller built the counting index), 4 CTAs/SM
-          if (pa.out4) go(k_pair_step<KIND, OPT, 128, 8, 4, false, true>, 8);
-          else go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8);
-          break;
-        case 8:   // same, 3 CTAs/SM (85 registers)
-          if (pa.out4) go(k_pair_step<KIND, OPT, 128, 8, 3, false, true>, 8);
-          else go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8);
-          break;
-        default: go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8); break;
-      }
+      if (LAZY) go(k_pair_step<KIND, OPT, 128, 8, 3, false>, 8);
+      else go(k_pair_step<KIND, OPT, 128, 8, 4, false>, 8);
       break;
     case 256: go(k_pair_step<KIND, OPT, 256, 8, 2, !LAZY>, 8); break;
     default: go(k_pair_step_generic<KIND, OPT>, 8); break;
@@ -1041,10 +649,10 @@ static int launch_pair_step_kind_opt(const PairArgs& pa, int n_warps_hint, cudaS
 template <int KIND>
 static int launch_pair_step_kind(const PairArgs& pa, int opt_kind, cudaStream_t st, int* n_partials) {
   switch (opt_kind) {
-    case ORX_OPT_SGD: return launch_pair_step_kind_opt<KIND, ORX_OPT_SGD>(pa, 0, st, n_partials);
-    case ORX_OPT_ADAGRAD: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAGRAD>(pa, 0, st, n_partials);
-    case ORX_OPT_ADAM_LAZY: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAM_LAZY>(pa, 0, st, n_partials);
-    case ORX_OPT_ADAM_DENSE: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAM_DENSE>(pa, 0, st, n_partials);
+    case ORX_OPT_SGD: return launch_pair_step_kind_opt<KIND, ORX_OPT_SGD>(pa, st, n_partials);
+    case ORX_OPT_ADAGRAD: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAGRAD>(pa, st, n_partials);
+    case ORX_OPT_ADAM_LAZY: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAM_LAZY>(pa, st, n_partials);
+    case ORX_OPT_ADAM_DENSE: return launch_pair_step_kind_opt<KIND, ORX_OPT_ADAM_DENSE>(pa, st, n_partials);
   }
   orx_set_error("unknown optimizer kind %d", opt_kind);
   return ORX_ERR_INVALID;
@@ -1063,25 +671,79 @@ static int check_tables(const orx_table_t* user, const orx_table_t* item, const 
   return ORX_OK;
 }
 
-// ORX_FUSED=0 selects the three-launch path (index / step / tail); default: fused persistent kernel where an
-// instance exists (D = 128, SGD / Adagrad).
-static bool pair_fused_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ORX_FUSED");
-    v = e ? atoi(e) : 0;   // opt-in: steady-state it is no faster than the 3-launch path (profiles/README.md r1g)
+// ---- pipelined batch index ------------------------------------------------------------------------------------------
+// The index of a batch depends only on its ids, so it can be built while the PREVIOUS step's kernels still run: on the
+// context's side stream, into one of two "prefetch" index sets (hash tables + counters) that alternate -- set 0 stays
+// with everything that builds its index on the caller's stream (pointwise / DLRM / censor / sharded / un-prefetched
+// pairwise steps).  The step that consumes a prefetched index waits for it with an event; the set is handed back with
+// an event recorded behind that step's tail.
+static int side_stream_ensure(orx_ctx* c) {
+  if (c->side_stream) return ORX_OK;
+  ORX_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    ORX_CUDA(cudaEventCreateWithFlags(&c->side_ev[i], cudaEventDisableTiming));
+    ORX_CUDA(cudaEventCreateWithFlags(&c->pf_done[i], cudaEventDisableTiming));
+    ORX_CUDA(cudaEventCreateWithFlags(&c->pf_free[i], cudaEventDisableTiming));
+    ORX_CUDA(cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming));
+    c->pf_free_valid[i] = c->stage_free_valid[i] = 0;
   }
-  return v != 0;
+  return ORX_OK;
 }
 
-// index_stream != nullptr (experimental, LA variants only): the index is built into the context's SECOND hash set on
-// that stream (behind whatever the caller queued there, e.g. the id upload), `st` waits for it, and the previous step --
-// which uses the first set -- may still be running on `st` meanwhile.  `set` alternates per call.
+// a prefetched index nobody consumed: wait for it, reset its counters (the hash itself dies with its epoch)
+static int prefetch_drop(orx_ctx* c, cudaStream_t st) {
+  if (!c->pf_valid) return ORX_OK;
+  const int k = c->pf_set;
+  ORX_CUDA(cudaStreamWaitEvent(st, c->pf_done[k], 0));
+  ORX_CUDA(cudaMemsetAsync(c->counters + 4 * (1 + k), 0, sizeof(int32_t) * 4, st));
+  ORX_CUDA(cudaEventRecord(c->pf_free[k], st));
+  c->pf_free_valid[k] = 1;
+  c->pf_valid = 0;
+  return ORX_OK;
+}
+
+// Build the index of (uid, pid, nid) on the side stream.  `after` (may be null) is an event the build must wait for
+// (the caller's "ids are final" point); the ids themselves may also be produced on the side stream (host upload).
+static int prefetch_issue(orx_ctx* c, const int32_t* uid, const int32_t* pid, const int32_t* nid, int B, int64_t rows_u,
+                          int64_t rows_i, int mode) {
+  const int k = c->pf_next;
+  c->pf_next ^= 1;
+  cudaStream_t ss = c->side_stream;
+  if (c->pf_free_valid[k]) ORX_CUDA(cudaStreamWaitEvent(ss, c->pf_free[k], 0));   // the step that last used set k is done
+  int rc = orx_next_epoch(c, ss);
+  if (rc) return rc;
+  c->pf_u[k].epoch = c->pf_i[k].epoch = c->epoch;
+  k_index_build<<<(3 * B + 255) / 256, 256, 0, ss>>>(c->pf_u[k], c->pf_i[k], uid, rows_u, B, pid, nid, rows_i, B, mode,
+                                                     c->counters + 4 * (1 + k) + 3);
+  ORX_LAUNCH_CHECK();
+  ORX_CUDA(cudaEventRecord(c->pf_done[k], ss));
+  c->pf_valid = 1; c->pf_set = k; c->pf_uid = uid; c->pf_pid = pid; c->pf_nid = nid; c->pf_B = B;
+  c->pf_rows_u = rows_u; c->pf_rows_i = rows_i; c->pf_mode = mode;
+  return ORX_OK;
+}
+
+extern "C" int orx_pairwise_prefetch(orx_handle_t h, const orx_table_t* user, const orx_table_t* item, const int32_t* uid,
+                                     const int32_t* pid, const int32_t* nid, int32_t B, int32_t opt_kind, int32_t ids_ready,
+                                     orx_stream_t ids_stream) {
+  ORX_REQUIRE(h != nullptr && user && item && uid && pid && nid && B > 0, "bad arguments");
+  ORX_REQUIRE(opt_kind >= ORX_OPT_SGD && opt_kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
+  ORX_CUDA(cudaSetDevice(h->device));
+  cudaStream_t is = (cudaStream_t)ids_stream;
+  int rc = orx_ensure_workspace(h, B, user->dim, false);
+  if (rc) return rc;
+  if ((rc = side_stream_ensure(h))) return rc;
+  if ((rc = prefetch_drop(h, is))) return rc;
+  if (!ids_ready) {   // the ids are final once everything queued on ids_stream so far has run
+    ORX_CUDA(cudaEventRecord(h->side_ev[0], is));
+    ORX_CUDA(cudaStreamWaitEvent(h->side_stream, h->side_ev[0], 0));
+  }
+  return prefetch_issue(h, uid, pid, nid, B, user->rows, item->rows, opt_kind == ORX_OPT_ADAM_DENSE ? 1 : 0);
+}
+
 static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, const orx_table_t* item,
                               const orx_table_t* bias, const int32_t* uid, const int32_t* pid, const int32_t* nid,
                               int B, float margin, float c_loss, float c_l2, const orx_opt_t* opt, float* out4,
-                              cudaStream_t st, int set = 0, cudaStream_t index_stream = nullptr,
-                              cudaEvent_t index_done = nullptr) {
+                              cudaStream_t st) {
   ORX_REQUIRE(kind == ORX_PAIR_BPR || kind == ORX_PAIR_UCML, "unknown pairwise kind");
   ORX_REQUIRE(opt != nullptr && out4 != nullptr, "null opt/out");
   ORX_REQUIRE(opt->kind >= ORX_OPT_SGD && opt->kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
@@ -1104,39 +766,20 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
   if ((rc = orx_ensure_partials(c, (B + 63) / 64 + 8 > c->num_sms ? (B + 63) / 64 + 8 : c->num_sms, st))) return rc;
   pa.partials = c->partials;
   orx_prof_mark(c, 0, st);
-  if (pair_fused_enabled()) {   // one persistent cooperative launch (orx_pair_fused.cu)
-    orx_new_epoch(c);
-    pa.hu = c->hu; pa.hi = c->hi;
-    orx_prof_mark(c, 1, st);     // all phases live inside one kernel: it is reported as the "step" phase
-    rc = orx_launch_pair_fused(c, kind, opt->kind, pa, kind == ORX_PAIR_BPR ? pa.inv_B : 1.0f, out4, st);
-    if (rc == ORX_OK) {
-      orx_prof_mark(c, 2, st);
-      orx_prof_mark(c, 3, st);
-      orx_prof_next(c);
-      return ORX_OK;
-    }
-    if (rc != ORX_ERR_UNSUPPORTED) return rc;
+  // index: a matching prefetched one (side stream, possibly still running), else built here on the caller's stream
+  int set = 0;
+  if (c->pf_valid && c->pf_uid == uid && c->pf_pid == pid && c->pf_nid == nid && c->pf_B == B &&
+      c->pf_rows_u == user->rows && c->pf_rows_i == item->rows && c->pf_mode == (dense ? 1 : 0)) {
+    set = 1 + c->pf_set;
+    ORX_CUDA(cudaStreamWaitEvent(st, c->pf_done[c->pf_set], 0));
+    c->pf_valid = 0;
+  } else {
+    if ((rc = prefetch_drop(c, st))) return rc;
+    if ((rc = orx_launch_index_build(c, uid, user->rows, B, pid, nid, item->rows, B, dense ? 1 : 0, st))) return rc;
   }
-  // experimental "last arriver applies" variants (D = 128, not Keras-dense Adam): reference-counted index, no tail
-  const bool la = D == 128 && !dense && opt->kind != ORX_OPT_ADAM_LAZY && (pair_variant() == 7 || pair_variant() == 8);
-  const bool second = la && set == 1;
-  if (second && (rc = orx_ensure_second_index(c))) return rc;
-  OrxHash& HU = second ? c->hu_b : c->hu;
-  OrxHash& HI = second ? c->hi_b : c->hi;
-  int32_t* ctr = second ? c->counters + 4 : c->counters;
-  pa.out4 = la ? out4 : nullptr; pa.counters = ctr; pa.loss_scale = (kind == ORX_PAIR_BPR) ? pa.inv_B : 1.0f;
-  cudaStream_t ist = (la && index_stream) ? index_stream : st;
-  if (index_stream && !la) {   // no overlap without the LA variants: just order `st` behind the caller's id upload
-    ORX_CUDA(cudaEventRecord(index_done, index_stream));
-    ORX_CUDA(cudaStreamWaitEvent(st, index_done, 0));
-  }
-  if ((rc = orx_launch_index_build_on(c, HU, HI, ctr, uid, user->rows, B, pid, nid, item->rows, B,
-                                      la ? 3 : (dense ? 1 : 0), ist)))
-    return rc;
-  if (index_stream && la) {    // upload + index ran on index_stream: `st` (the step kernel) waits for both
-    ORX_CUDA(cudaEventRecord(index_done, index_stream));
-    ORX_CUDA(cudaStreamWaitEvent(st, index_done, 0));
-  }
+  const OrxHash& HU = set ? c->pf_u[set - 1] : c->hu;
+  const OrxHash& HI = set ? c->pf_i[set - 1] : c->hi;
+  int32_t* ctr = c->counters + 4 * set;
   orx_prof_mark(c, 1, st);
   pa.hu = HU; pa.hi = HI;
   int n_partials = 0;
@@ -1144,27 +787,26 @@ static int pairwise_step_impl(orx_ctx* c, int kind, const orx_table_t* user, con
                               : launch_pair_step_kind<ORX_PAIR_UCML>(pa, opt->kind, st, &n_partials);
   if (rc) return rc;
   orx_prof_mark(c, 2, st);
-  if (la) {   // the step kernel's own epilogue wrote out4 and reset the counters
-    orx_prof_mark(c, 3, st);
-    orx_prof_next(c);
-    return ORX_OK;
-  }
   if (dense) {
-    if ((rc = orx_launch_adam_sweep(c, user->var, user->s0, user->s1, user->rows, D, c->hu, c->gu, pa.opt, st))) return rc;
-    if ((rc = orx_launch_adam_sweep(c, item->var, item->s0, item->s1, item->rows, D, c->hi, c->gi, pa.opt, st))) return rc;
-    if ((rc = orx_launch_adam_sweep(c, bias->var, bias->s0, bias->s1, bias->rows, 1, c->hi, c->gb, pa.opt, st))) return rc;
+    if ((rc = orx_launch_adam_sweep(c, user->var, user->s0, user->s1, user->rows, D, HU, c->gu, pa.opt, st))) return rc;
+    if ((rc = orx_launch_adam_sweep(c, item->var, item->s0, item->s1, item->rows, D, HI, c->gi, pa.opt, st))) return rc;
+    if ((rc = orx_launch_adam_sweep(c, bias->var, bias->s0, bias->s1, bias->rows, 1, HI, c->gb, pa.opt, st))) return rc;
   }
   TailArgs ta;
   ta.U = user->var; ta.Us0 = user->s0; ta.Us1 = user->s1;
   ta.I = item->var; ta.Is0 = item->s0; ta.Is1 = item->s1;
   ta.Bv = bias->var; ta.Bs0 = bias->s0; ta.Bs1 = bias->s1;
-  ta.D = D; ta.opt = pa.opt; ta.hu = c->hu; ta.hi = c->hi;
+  ta.D = D; ta.opt = pa.opt; ta.hu = HU; ta.hi = HI;
   ta.gu = c->gu; ta.gi = c->gi; ta.gb = c->gb;
   ta.partials = c->partials; ta.n_partials = n_partials;
   ta.loss_scale = (kind == ORX_PAIR_BPR) ? pa.inv_B : 1.0f;
-  ta.counters = c->counters; ta.out4 = out4;
+  ta.counters = ctr; ta.out4 = out4;
   ta.W = ta.Ws0 = ta.Ws1 = ta.gw = nullptr; ta.c_l2 = c_l2;
   rc = orx_launch_tail(c, ta, opt->kind, st);
+  if (set) {   // the prefetch set is free again once this tail has run
+    ORX_CUDA(cudaEventRecord(c->pf_free[set - 1], st));
+    c->pf_free_valid[set - 1] = 1;
+  }
   orx_prof_mark(c, 3, st);
   orx_prof_next(c);
   return rc;
@@ -1180,73 +822,38 @@ extern "C" int orx_pairwise_step(orx_handle_t h, int32_t kind, const orx_table_t
                             (cudaStream_t)s);
 }
 
+// Host-buffer form: the upload of this batch's ids and its index build run on the side stream, i.e. under the previous
+// step's kernels whenever the caller enqueues ahead of the GPU; the step kernels and the read-back of out4 stay on `s`.
+// The id staging buffers alternate; buffer f is reused only after the step that read it has finished (stage_free[f]).
 extern "C" int orx_pairwise_step_host(orx_handle_t h, int32_t kind, const orx_table_t* user, const orx_table_t* item,
                                       const orx_table_t* item_bias, const int32_t* uid_host, const int32_t* pid_host,
                                       const int32_t* nid_host, int32_t B, float margin, float c_loss, float c_l2,
                                       const orx_opt_t* opt, float* out4_host, orx_stream_t s) {
   ORX_REQUIRE(h != nullptr, "null handle");
-  ORX_REQUIRE(B > 0 && uid_host && pid_host && nid_host && out4_host, "empty batch or null host buffers");
+  ORX_REQUIRE(B > 0 && uid_host && pid_host && nid_host && out4_host && user && item && opt, "empty batch or null host buffers");
   ORX_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)s;
   int rc = orx_ensure_stage(h, 3 * (int64_t)B);
   if (rc) return rc;
+  if ((rc = orx_ensure_workspace(h, B, user->dim, false))) return rc;
+  if ((rc = side_stream_ensure(h))) return rc;
+  if ((rc = prefetch_drop(h, st))) return rc;
   const uint32_t f = (h->stage_flip++) & 1u;
   int32_t* ids = h->ids_stage[f];
-  static int use_copy_stream = -1;
-  if (use_copy_stream < 0) {
-    const char* e = getenv("ORX_HOST_COPY_STREAM");
-    use_copy_stream = (e && atoi(e)) ? 1 : 0;
-  }
-  if (use_copy_stream) {
-    // experimental: the upload of this batch runs on a copy stream, i.e. under the previous step's kernels when the
-    // caller enqueues ahead.  ids_stage[f] was last read by the step two calls ago: wait for that step first.
-    if (!h->copy_stream) {
-      ORX_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-      for (int i = 0; i < 2; ++i) {
-        ORX_CUDA(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
-        ORX_CUDA(cudaEventCreateWithFlags(&h->stage_free[i], cudaEventDisableTiming));
-        h->stage_free_valid[i] = 0;
-      }
-    }
-    cudaStream_t cs = h->copy_stream;
-    if (h->stage_free_valid[f]) ORX_CUDA(cudaStreamWaitEvent(cs, h->stage_free[f], 0));
-    if (pid_host == uid_host + B && nid_host == pid_host + B) {   // one contiguous (uid | pid | nid) host block
-      ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * 3 * (size_t)B, cudaMemcpyHostToDevice, cs));
-    } else {
-      ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
-      ORX_CUDA(cudaMemcpyAsync(ids + B, pid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
-      ORX_CUDA(cudaMemcpyAsync(ids + 2 * (int64_t)B, nid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
-    }
-    static int overlap_index = -1;
-    if (overlap_index < 0) {
-      const char* e = getenv("ORX_OVERLAP_INDEX");
-      overlap_index = (e && atoi(e)) ? 1 : 0;
-    }
-    if (overlap_index) {
-      // experimental: the index build follows the upload on the copy stream into hash set f, so with the LA variants
-      // (no tail) it runs beside the previous step's k_pair_step, which uses the other set
-      rc = pairwise_step_impl(h, kind, user, item, item_bias, ids, ids + B, ids + 2 * (int64_t)B, B, margin, c_loss,
-                              c_l2, opt, h->out_stage[f], st, (int)f, cs, h->copy_done[f]);
-      if (rc) return rc;
-      ORX_CUDA(cudaEventRecord(h->stage_free[f], st));
-      h->stage_free_valid[f] = 1;
-      ORX_CUDA(cudaMemcpyAsync(out4_host, h->out_stage[f], sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
-      return ORX_OK;
-    }
-    ORX_CUDA(cudaEventRecord(h->copy_done[f], cs));
-    ORX_CUDA(cudaStreamWaitEvent(st, h->copy_done[f], 0));
-  } else {
-    ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-    ORX_CUDA(cudaMemcpyAsync(ids + B, pid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-    ORX_CUDA(cudaMemcpyAsync(ids + 2 * (int64_t)B, nid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, st));
-  }
+  cudaStream_t ss = h->side_stream;
+  if (h->stage_free_valid[f]) ORX_CUDA(cudaStreamWaitEvent(ss, h->stage_free[f], 0));
+  // three copies: the caller's arrays are separate (pinned) allocations even when they happen to be adjacent
+  ORX_CUDA(cudaMemcpyAsync(ids, uid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, ss));
+  ORX_CUDA(cudaMemcpyAsync(ids + B, pid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, ss));
+  ORX_CUDA(cudaMemcpyAsync(ids + 2 * (int64_t)B, nid_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, ss));
+  if ((rc = prefetch_issue(h, ids, ids + B, ids + 2 * (int64_t)B, B, user->rows, item->rows,
+                           opt->kind == ORX_OPT_ADAM_DENSE ? 1 : 0)))
+    return rc;
   rc = pairwise_step_impl(h, kind, user, item, item_bias, ids, ids + B, ids + 2 * (int64_t)B, B, margin, c_loss, c_l2,
                           opt, h->out_stage[f], st);
   if (rc) return rc;
-  if (use_copy_stream) {
-    ORX_CUDA(cudaEventRecord(h->stage_free[f], st));
-    h->stage_free_valid[f] = 1;
-  }
+  ORX_CUDA(cudaEventRecord(h->stage_free[f], st));
+  h->stage_free_valid[f] = 1;
   ORX_CUDA(cudaMemcpyAsync(out4_host, h->out_stage[f], sizeof(float) * 4, cudaMemcpyDeviceToHost, st));
   return ORX_OK;
 }

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) k_sparse_apply_tail(float* var, float* s0
 
 static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
                              const float* values, int64_t value_ld, int32_t n, const int32_t* n_dev,
-                             const orx_opt_t* opt, orx_stream_t s, bool index_prebuilt = false);
+                             const orx_opt_t* opt, orx_stream_t s);
 
 extern "C" int orx_sparse_apply(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
                                 int32_t n, const orx_opt_t* opt, orx_stream_t s) {
@@ -243,26 +243,9 @@ extern "C" int orx_sparse_apply_strided(orx_handle_t h, const orx_table_t* tab, 
   return sparse_apply_impl(h, tab, ids, id_stride, values, value_ld, n, nullptr, opt, s);
 }
 
-// Same, but the number of (id, value-row) pairs is only known on the device (*n_dev <= n_max): the mailbox exchange's
-// owner side (orx_xchg.cu), where the count is the sum of what the peers pushed.  No host round trip.
-extern "C" int orx_sparse_apply_devn(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
-                                     int64_t value_ld, int32_t n_max, const int32_t* n_dev, const orx_opt_t* opt,
-                                     orx_stream_t s) {
-  ORX_REQUIRE(tab != nullptr && n_dev != nullptr && value_ld >= tab->dim && n_max > 0, "bad arguments");
-  return sparse_apply_impl(h, tab, ids, 1, values, value_ld, n_max, n_dev, opt, s);
-}
-
-// orx_xchg_step builds the index of the owner's ids on a side stream while the gradient rows are still in flight,
-// then calls this with index_prebuilt = true (same workspace, same epoch).
-int orx_sparse_apply_prebuilt(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, const float* values,
-                              int64_t value_ld, int32_t n_max, const int32_t* n_dev, const orx_opt_t* opt,
-                              cudaStream_t st) {
-  return sparse_apply_impl(h, tab, ids, 1, values, value_ld, n_max, n_dev, opt, (orx_stream_t)st, true);
-}
-
 static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32_t* ids, int64_t id_stride,
                              const float* values, int64_t value_ld, int32_t n, const int32_t* n_dev,
-                             const orx_opt_t* opt, orx_stream_t s, bool index_prebuilt) {
+                             const orx_opt_t* opt, orx_stream_t s) {
   ORX_REQUIRE(h != nullptr && tab && tab->var && opt, "null pointer");
   ORX_REQUIRE(n >= 0 && tab->rows > 0 && tab->dim > 0, "bad sizes");
   ORX_REQUIRE(opt->kind >= ORX_OPT_SGD && opt->kind <= ORX_OPT_ADAM_DENSE, "unknown optimizer kind");
@@ -279,8 +262,7 @@ static int sparse_apply_impl(orx_handle_t h, const orx_table_t* tab, const int32
   const OrxOptDev o = orx_opt_to_dev(opt);
   // the user-side hash / staging pair serves as "the" table here
   if (n > 0) {
-    if (!index_prebuilt)
-      if ((rc = orx_launch_index_build_strided(h, ids, id_stride, tab->rows, n, n_dev, dense, st))) return rc;
+    if ((rc = orx_launch_index_build_strided(h, ids, id_stride, tab->rows, n, n_dev, dense, st))) return rc;
     int blocks = (n + 63) / 64;   // 8 warps x 8 pairs per block and iteration
     if (n_dev && blocks > h->num_sms * 8) blocks = h->num_sms * 8;
     switch (opt->kind) {

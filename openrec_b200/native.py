@@ -117,6 +117,17 @@ class Engine:
                                                    c_loss, c_l2, C.byref(o), _ptr(out4_h), self.stream()),
                    "orx_pairwise_step_host")
 
+    def pairwise_prefetch(self, user, item, uid, pid, nid, opt_kind, ids_ready=False):
+        """Pipelining hint: build the batch index of these id tensors on the side stream now (the next pairwise_step
+        with these very tensors consumes it).  ids_ready=True: the tensors are already complete (pre-staged batches),
+        so the build does not wait for anything queued on the current stream."""
+        _lib.check(self.lib.orx_pairwise_prefetch(self.h, C.byref(user), C.byref(item), _ptr(uid), _ptr(pid), _ptr(nid),
+                                                  uid.numel(), opt_kind, 1 if ids_ready else 0, self.stream()),
+                   "orx_pairwise_prefetch")
+
+    def debug_set_epoch(self, epoch):
+        _lib.check(self.lib.orx_debug_set_epoch(self.h, epoch), "orx_debug_set_epoch")
+
     def pairwise_fwd(self, kind, user, item, bias, uid, pid, nid, out4, margin=0.5):
         _lib.check(self.lib.orx_pairwise_fwd(self.h, kind, C.byref(user), C.byref(item), C.byref(bias), _ptr(uid),
                                              _ptr(pid), _ptr(nid), uid.numel(), margin, _ptr(out4), self.stream()),

@@ -122,118 +122,203 @@ class ShardedPairwise:
         return outs
 
 
-class MailboxShardedPairwise(ShardedPairwise):
-    """Same partitioning and arithmetic as ShardedPairwise, but the three exchanges are liborx kernels that STORE into
-    the peers' mailboxes over NVLink (CUDA IPC mappings; csrc/orx_xchg.cu) -- no NCCL in the data path, no host sync.
-    ``torch.distributed`` is used once to swap the IPC handles, and (``barrier="nccl"``) for the three tiny
-    stream-ordered barriers of a step; ``barrier="flag"`` uses orx_xchg_barrier (flags in peer memory) instead.
+class _PeerBuf:
+    """A cudaMalloc'd, IPC-exportable device buffer viewed as a torch tensor (orx_peer_alloc)."""
 
-    Buffer reuse across steps is ordered by the same barriers: idbox is rewritten after C(t) and read before B(t);
-    got is rewritten after A(t+1) and read before C(t); gin is rewritten after B(t+1) and read by the owner's apply
-    of step t, which precedes its arrival at A(t+1)."""
+    def __init__(self, eng, n_elems, dtype):
+        self.eng = eng
+        n = max(int(n_elems), 4)
+        self.bytes = n * 4
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(eng.lib.orx_peer_alloc(eng.h, self.bytes, C.byref(ptr), handle), "orx_peer_alloc")
+        self.ptr, self.handle = ptr.value, handle.raw
+        typestr = {torch.float32: "<f4", torch.int32: "<i4"}[dtype]
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+        self.t = torch.as_tensor(self, device=eng.device)     # zero-copy view of our own allocation
 
-    def __init__(self, eng, rank, world, total_users, total_items, dim, batch, *, barrier=None, gin_rows=None, **kw):
-        super().__init__(eng, rank, world, total_users, total_items, dim, **kw)
-        from .sharded_peer import _PeerBuf
-        if dim % 4:
-            raise ValueError("the mailbox exchange needs dim % 4 == 0")
-        self.B = batch
-        self.cap = 3 * batch
-        self.gin_rows = int(gin_rows or world * self.cap)        # worst case: every rank's lookups land on me
-        self.barrier_kind = barrier or os.environ.get("ORX_XCHG_BARRIER", "flag")
+    def free(self):
+        if self.ptr:
+            self.t = None
+            self.eng.lib.orx_peer_free(self.eng.h, C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+_MAILBOX_DTYPES = (torch.int32, torch.int32, torch.float32, torch.float32, torch.float32, torch.float32, torch.int32,
+                   torch.int32)   # tripbox idbox got gotb gin ginb meta flags
+_SHARD_ERRORS = {1: "a peer rank never arrived (flag wait timed out)",
+                 2: "more triplets were routed to this rank than home_cap: rebuild with a larger home_cap",
+                 3: "one owner received more requests than req_cap", 4: "gradient inbox overflow: rebuild with a larger gin_cap"}
+
+
+class HomeRoutedPairwise:
+    """Row-sharded BPR (kind 0) / UCML (kind 1) step, "home-routed" (csrc/orx_shard.cu): row r of the user and item
+    tables lives on rank ``r % R``; a triplet is computed on the rank that owns its USER row, so only the two item rows
+    travel in and the two item gradient rows travel out, as peer stores of aligned rows into IPC-mapped mailboxes.  One
+    C call per step (seven launches, flag words in peer memory instead of barriers, no collective, no host sync).
+    ``torch.distributed`` is used once, to swap the 64-byte IPC handles.
+
+    ``peers=None``: the R ranks are R processes (one per GPU) and the mailboxes are exchanged over ``torch.distributed``.
+    ``peers=<LoopbackGroup>``: R virtual ranks share one device and one stream (1-GPU parity test of the same kernels).
+    """
+
+    def __init__(self, eng, rank, world, total_users, total_items, dim, batch, *, kind=0, opt_kind=1, lr=0.05, eps=1e-7,
+                 beta1=0.9, beta2=0.999, margin=0.5, seed=0, init=True, home_cap=None, gin_cap=None, timeout_ms=20000,
+                 peers=None):
+        if dim % 4 or dim > 512:
+            raise ValueError("the sharded step needs dim % 4 == 0 and dim <= 512")
+        if opt_kind not in (0, 1, 2):
+            raise ValueError("the sharded step supports SGD, Adagrad and row-sparse Adam")
+        self.eng, self.rank, self.world = eng, rank, world
+        self.U, self.I, self.D, self.B = total_users, total_items, dim, batch
+        self.kind, self.opt_kind, self.lr, self.eps, self.b1, self.b2, self.margin = kind, opt_kind, lr, eps, beta1, beta2, margin
+        self.iterations = 0
         dev = eng.device
-        W = self.W
-        self._bufs = [_PeerBuf(eng, (world * self.cap,), torch.int32),      # idbox
-                      _PeerBuf(eng, (world * 8,), torch.int32),             # meta
-                      _PeerBuf(eng, (self.cap, W), torch.float32),          # got
-                      _PeerBuf(eng, (self.gin_rows, W), torch.float32),     # gin
-                      _PeerBuf(eng, (world + 1,), torch.int32)]             # flags
-        for b in self._bufs:
-            b.t.zero_()
-        torch.cuda.synchronize()
-        everyone = [None] * world
-        dist.all_gather_object(everyone, [b.handle for b in self._bufs])
+        self.ru = (total_users - rank + world - 1) // world     # rows r with r % world == rank
+        self.ri = (total_items - rank + world - 1) // world
+        self.user = torch.zeros(max(self.ru, 1), dim, dtype=torch.float32, device=dev)
+        self.item = torch.zeros(max(self.ri, 1), dim, dtype=torch.float32, device=dev)
+        self.bias = torch.zeros(max(self.ri, 1), 1, dtype=torch.float32, device=dev)
+        if init:
+            for k, t in enumerate((self.user, self.item, self.bias)):
+                eng.fill_uniform(t, -0.05, 0.05, seed * 1000003 + rank * 17 + k)
+        n_slots = {0: 0, 1: 1, 2: 2}[opt_kind]
+        fill = 0.1 if opt_kind == 1 else 0.0
+        mk = lambda t: [torch.full_like(t, fill) for _ in range(n_slots)] + [None] * (2 - n_slots)
+        self.user_slots, self.item_slots, self.bias_slots = mk(self.user), mk(self.item), mk(self.bias)
+        # capacities: worst case for small problems (tests), 2x the expected load for big ones (errors are sticky flags)
+        small = world * batch <= (1 << 16)
+        self.home_cap = int(home_cap or (world * batch if small else 2 * batch))
+        self.req_cap = 2 * self.home_cap
+        self.gin_cap = int(gin_cap or (world * (2 * self.home_cap + 32) if small else 4 * batch + 32 * world))
+        self.gin_cap = (self.gin_cap + 31) // 32 * 32
+        self._x = _lib.OrxShard(world, rank, dim, batch, self.home_cap, self.req_cap, self.gin_cap, timeout_ms,
+                                0, 0, 0, 0, 0, 0, 0, 0)
+        sizes = (C.c_int64 * 8)()
+        _lib.check(eng.lib.orx_shard_sizes(C.byref(self._x), sizes), "orx_shard_sizes")
+        self._loop = peers
         self._opened = []
-        ptrs = np.zeros((5, world), dtype=np.int64)
-        for r in range(world):
-            for k in range(5):
-                if r == rank:
-                    ptrs[k, r] = self._bufs[k].ptr
-                else:
-                    p = C.c_void_p()
-                    _lib.check(eng.lib.orx_peer_open(eng.h, everyone[r][k], C.byref(p)), "orx_peer_open")
-                    self._opened.append(p.value)
-                    ptrs[k, r] = p.value
-        self._ptrs = torch.from_numpy(ptrs).to(dev)
+        if peers is None:
+            self._bufs = [_PeerBuf(eng, sizes[k], _MAILBOX_DTYPES[k]) for k in range(8)]
+            mine = [b.ptr for b in self._bufs]
+            torch.cuda.synchronize()
+            everyone = [None] * world
+            dist.all_gather_object(everyone, [b.handle for b in self._bufs])
+            ptrs = np.zeros((8, world), dtype=np.int64)
+            for r in range(world):
+                for k in range(8):
+                    if r == rank:
+                        ptrs[k, r] = mine[k]
+                    else:
+                        p = C.c_void_p()
+                        _lib.check(eng.lib.orx_peer_open(eng.h, everyone[r][k], C.byref(p)), "orx_peer_open")
+                        self._opened.append(p.value)
+                        ptrs[k, r] = p.value
+            self._set_pointers(ptrs)
+            dist.barrier()
+        else:                    # loopback: plain device memory, the group wires the pointer tables
+            self._bufs = None
+            self._tensors = [torch.zeros(max(int(sizes[k]), 4), dtype=_MAILBOX_DTYPES[k], device=dev) for k in range(8)]
+            peers._register(self)
+        self._out = torch.zeros(16, 4, dtype=torch.float32, device=dev)     # ring of step outputs
+        self._tabs = (eng.make_table(self.user, *self.user_slots), eng.make_table(self.item, *self.item_slots),
+                      eng.make_table(self.bias, *self.bias_slots))
+        self.launches_per_step = 7
+
+    def _set_pointers(self, ptrs):
+        self._ptrs = torch.from_numpy(np.ascontiguousarray(ptrs)).to(self.eng.device)
         base = self._ptrs.data_ptr()
-        self._x = _lib.OrxXchg(world, rank, W, self.cap, *[base + 8 * world * k for k in range(5)])
-        self._req = torch.empty(self.gin_rows, dtype=torch.int32, device=dev)
-        self._n_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._epoch = 0
-        self._work = torch.zeros(world + 1 + ((self.cap + 1023) // 1024) * world, dtype=torch.int32, device=dev)
-        self._slot = torch.empty(self.cap, dtype=torch.int32, device=dev)
-        self._out = torch.zeros(16, 4, dtype=torch.float32, device=dev)     # ring of step outputs (loss, l2, -, -)
-        self.fused_call = os.environ.get("ORX_XCHG_FUSED", "1") != "0" and self.barrier_kind == "flag"
-        self.launches_per_step = 2 + 1 + 2 + 3 + 3 + 1   # hist, scatter+push, gather+push, grads+loss push, apply(3), 3 barriers, loss sum
-        dist.barrier()
+        for k, name in enumerate(("tripbox", "idbox", "got", "gotb", "gin", "ginb", "meta", "flags")):
+            setattr(self._x, name, base + 8 * self.world * k)
 
-    def _barrier(self):
-        if self.barrier_kind == "flag":
-            self._epoch += 1
-            _lib.check(self.eng.lib.orx_xchg_barrier(self.eng.h, C.byref(self._x), self._epoch, 5000, self.eng.stream()),
-                       "orx_xchg_barrier")
-        else:
-            dist.all_reduce(self._flag)
+    def _flags(self):
+        return self._bufs[7].t if self._bufs is not None else self._tensors[7]
 
-    def step(self, uid, pid, nid, c_loss=1.0, c_l2=1.0, reduce_loss=True):
-        eng, R, D, W = self.eng, self.world, self.D, self.W
+    def _call(self, uid, pid, nid, c_loss, c_l2, lo, hi):
+        eng = self.eng
         B = uid.numel()
         if B > self.B:
             raise ValueError("batch larger than the mailboxes this model was built for")
-        self.iterations += 1
-        x, st = C.byref(self._x), eng.stream()
-        vp = lambda t: C.c_void_p(t.data_ptr())
-        if self.fused_call:       # one C call: bucket + push, gather + push, grads + push, apply, 3 flag barriers
-            out4 = self._out[self.iterations % 16]
-            o = eng.make_opt(self.opt_kind, self.lr, self.eps, self.b1, self.b2, self.iterations)
-            tab = eng.make_table(self.table, *self.slots)
-            _lib.check(eng.lib.orx_xchg_step(eng.h, self.kind, x, C.byref(tab), vp(uid), vp(pid), vp(nid), B, self.U, D,
-                                             C.c_void_p(self._bufs[3].ptr), self.gin_rows, vp(self._work),
-                                             vp(self._slot), vp(self._req), self.margin, c_loss, c_l2, 1.0 / (B * R),
-                                             C.byref(o), self._epoch, 5000, vp(out4), st), "orx_xchg_step")
-            self._epoch += 3
-            return out4[:2]        # already the global (loss, l2_loss): the partials travel through the mailboxes
-        ids = torch.cat([uid, pid, nid])
-        counts, send_local, slot = eng.owner_bucket_combined(ids, B, self.U, R)
-        _lib.check(eng.lib.orx_xchg_push_ids(eng.h, x, vp(counts), vp(send_local), 3 * B, st), "orx_xchg_push_ids")
-        self._barrier()                                                # A: every owner has its requests
-        _lib.check(eng.lib.orx_xchg_gather_push(eng.h, x, vp(self.table), self.table.shape[0], self.gin_rows,
-                                                vp(self._req), vp(self._n_dev), None, st), "orx_xchg_gather_push")
-        self._barrier()                                                # B: my rows (and inbox bases) have landed
-        out4 = torch.zeros(4, dtype=torch.float32, device=uid.device)
-        _lib.check(eng.lib.orx_xchg_grad_push(eng.h, self.kind, x, vp(counts), vp(slot), B, D, self.margin, c_loss, c_l2,
-                                              1.0 / (B * R), vp(out4), st), "orx_xchg_grad_push")
-        self._barrier()                                                # C: every gradient row is in its owner's inbox
+        out4 = self._out[self.iterations % 16]
         o = eng.make_opt(self.opt_kind, self.lr, self.eps, self.b1, self.b2, self.iterations)
-        tab = eng.make_table(self.table, *self.slots)
-        _lib.check(eng.lib.orx_sparse_apply_devn(eng.h, C.byref(tab), vp(self._req), C.c_void_p(self._bufs[3].ptr), W,
-                                                 self.gin_rows, vp(self._n_dev), C.byref(o), st),
-                   "orx_sparse_apply_devn")
-        out = out4[:2].clone()
-        if reduce_loss:
-            dist.all_reduce(out)
-        return out
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        _lib.check(eng.lib.orx_shard_step(eng.h, self.kind, C.byref(self._x), C.byref(self._tabs[0]), C.byref(self._tabs[1]),
+                                          C.byref(self._tabs[2]), vp(uid), vp(pid), vp(nid), B, self.U, self.I, self.margin,
+                                          c_loss, c_l2, 1.0 / (B * self.world), C.byref(o), self.iterations, lo, hi, vp(out4),
+                                          eng.stream()), "orx_shard_step")
+        return out4
+
+    def step(self, uid, pid, nid, c_loss=1.0, c_l2=1.0, reduce_loss=True):
+        """uid/pid/nid: this rank's int32 GLOBAL ids on the device (every rank must pass the same batch size).
+        Returns a [2] device tensor = the GLOBAL (loss, l2_loss): the partials ride the meta mailboxes."""
+        if self._loop is not None:
+            raise RuntimeError("loopback ranks are stepped by their LoopbackGroup")
+        self.iterations += 1
+        return self._call(uid, pid, nid, c_loss, c_l2, 0, 6)[:2]
 
     def check(self):
-        """Raise if a barrier timed out or a gradient inbox overflowed (sticky device flag; one tiny D2H read)."""
-        code = int(self._bufs[4].t[self.world].item())
+        """Raise if a flag wait timed out or a mailbox overflowed (sticky device word; one tiny D2H read)."""
+        code = int(self._flags()[4 * 64].item())
         if code:
-            raise RuntimeError({1: "mailbox barrier timed out: a peer rank never arrived",
-                                2: "gradient inbox overflow: rebuild with a larger gin_rows"}.get(code, f"error {code}"))
+            raise RuntimeError("sharded step: " + _SHARD_ERRORS.get(code, f"error {code}"))
+
+    # ---- global <-> shard (tests, checkpoints)
+    def load_global(self, user, item, bias):
+        r, R = self.rank, self.world
+        dev = self.eng.device
+        self.user[:self.ru] = torch.as_tensor(np.ascontiguousarray(user[r::R]), dtype=torch.float32).to(dev)
+        self.item[:self.ri] = torch.as_tensor(np.ascontiguousarray(item[r::R]), dtype=torch.float32).to(dev)
+        self.bias[:self.ri] = torch.as_tensor(np.ascontiguousarray(bias[r::R]), dtype=torch.float32).reshape(-1, 1).to(dev)
+
+    def local_shards(self):
+        return self.user[:self.ru], self.item[:self.ri], self.bias[:self.ri]
+
+    def gather_global(self):
+        """-> (user, item, bias) full tables on every rank (test helper; sizes must be small)."""
+        outs = []
+        for t, total in zip(self.local_shards(), (self.U, self.I, self.I)):
+            per = (total + self.world - 1) // self.world
+            pad = torch.zeros(per, t.shape[1], dtype=t.dtype, device=t.device)
+            pad[:t.shape[0]] = t
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(parts, pad)
+            outs.append(torch.stack(parts, 1).reshape(per * self.world, t.shape[1])[:total])   # row = local*R + rank
+        return outs
+
+    # ---- per-rank shard checkpoint (SURVEY 8f N4 for tables that only exist sharded)
+    def save_shard(self, path):
+        """Write this rank's rows + optimizer slots + step count to ``path`` (one .npz per rank)."""
+        arrs = {"meta": np.array([self.rank, self.world, self.U, self.I, self.D, self.kind, self.opt_kind, self.iterations],
+                                 dtype=np.int64)}
+        for name, t, slots in (("user", self.user[:self.ru], self.user_slots), ("item", self.item[:self.ri], self.item_slots),
+                               ("bias", self.bias[:self.ri], self.bias_slots)):
+            arrs[name] = t.cpu().numpy()
+            for k, s in enumerate(slots):
+                if s is not None:
+                    arrs[f"{name}_s{k}"] = s[:t.shape[0]].cpu().numpy()
+        np.savez(path, **arrs)
+
+    def load_shard(self, path):
+        z = np.load(path)
+        meta = z["meta"].tolist()
+        want = [self.rank, self.world, self.U, self.I, self.D, self.kind, self.opt_kind]
+        if meta[:7] != want:
+            raise ValueError(f"shard checkpoint {path} was written for (rank, world, U, I, D, kind, opt) = {meta[:7]}, "
+                             f"this model is {want}")
+        dev = self.eng.device
+        for name, t, slots in (("user", self.user[:self.ru], self.user_slots), ("item", self.item[:self.ri], self.item_slots),
+                               ("bias", self.bias[:self.ri], self.bias_slots)):
+            t.copy_(torch.from_numpy(z[name]).to(dev))
+            for k, s in enumerate(slots):
+                if s is not None:
+                    s[:t.shape[0]].copy_(torch.from_numpy(z[f"{name}_s{k}"]).to(dev))
+        self.iterations = int(meta[7])
 
     def close(self):
         torch.cuda.synchronize()
+        if self._bufs is None:
+            return
         dist.barrier()
         for p in self._opened:
             self.eng.lib.orx_peer_close(self.eng.h, C.c_void_p(p))
@@ -241,6 +326,66 @@ class MailboxShardedPairwise(ShardedPairwise):
         dist.barrier()
         for b in self._bufs:
             b.free()
+        self._bufs = None
+
+
+class LoopbackGroup:
+    """R virtual ranks of HomeRoutedPairwise on ONE device and ONE stream: every rank has its own liborx handle, tables
+    and mailboxes (plain device memory); a step issues phase k of the seven launches for every rank before phase k + 1,
+    so every flag a kernel waits for is already set.  Same kernels, same peer-pointer tables as the multi-GPU step."""
+
+    def __init__(self, world, total_users, total_items, dim, batch, device=None, **kw):
+        from . import native
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.world = world
+        self.ranks = []
+        self._engines = [native.Engine(dev.index or 0) for _ in range(world)]
+        for r in range(world):
+            HomeRoutedPairwise(self._engines[r], r, world, total_users, total_items, dim, batch, peers=self, **kw)
+        ptrs = np.zeros((8, world), dtype=np.int64)
+        for r, m in enumerate(self.ranks):
+            for k in range(8):
+                ptrs[k, r] = m._tensors[k].data_ptr()
+        for m in self.ranks:
+            m._set_pointers(ptrs)
+        torch.cuda.synchronize()
+
+    def _register(self, m):
+        self.ranks.append(m)
+
+    def step(self, batches, c_loss=1.0, c_l2=1.0):
+        """batches[r] = (uid, pid, nid) of rank r.  Returns the [2] global (loss, l2_loss) tensor of every rank."""
+        for m in self.ranks:
+            m.iterations += 1
+        outs = [None] * self.world
+        for ph in range(7):
+            for r, m in enumerate(self.ranks):
+                outs[r] = m._call(*batches[r], c_loss, c_l2, ph, ph)
+        return [o[:2] for o in outs]
+
+    def load_global(self, user, item, bias):
+        for m in self.ranks:
+            m.load_global(user, item, bias)
+
+    def gather_global(self):
+        R = self.world
+        outs = []
+        for k, total in enumerate((self.ranks[0].U, self.ranks[0].I, self.ranks[0].I)):
+            shards = [m.local_shards()[k] for m in self.ranks]
+            full = torch.zeros(total, shards[0].shape[1], dtype=torch.float32, device=shards[0].device)
+            for r in range(R):
+                full[r::R] = shards[r]
+            outs.append(full)
+        return outs
+
+    def check(self):
+        for m in self.ranks:
+            m.check()
+
+    def close(self):
+        torch.cuda.synchronize()
+        for e in self._engines:
+            e.close()
 
 
 # ---------------------------------------------------------------------------------------
@@ -252,16 +397,10 @@ def bench(args, rank, world, eng, barrier):
     K, W = args.steps, max(3, args.warmup)
     dev = eng.device
     U, I, D, Bsz = B.U, 12_500_000 * world, B.D, B.B      # BASELINE configs[4]: 100M items x 128 over 8 GPUs
-    # Default: NCCL all-to-all exchange.  ORX_SHARDED=peer selects the one-sided NVLink peer-memory step
-    # (sharded_peer.py) -- correct, and fast while a rank's shard stays below ~2 GB, but random 512 B rows from a
-    # 6.6 GB peer-mapped shard run at 35 GB/s (vs ~600 GB/s at 2 GB; profiles/r1k_p2p_probe.txt), so it is opt-in.
-    mode = os.environ.get("ORX_SHARDED", "mailbox")
-    use_peer = mode == "peer"
-    if mode == "mailbox":
-        model = MailboxShardedPairwise(eng, rank, world, U, I, D, Bsz, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
-    elif use_peer:
-        from .sharded_peer import PeerShardedPairwise
-        model = PeerShardedPairwise(eng, rank, world, U, I, D, Bsz, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
+    # Default: the home-routed peer-store exchange (csrc/orx_shard.cu); ORX_SHARDED=nccl selects the NCCL all-to-all form
+    mode = os.environ.get("ORX_SHARDED", "home")
+    if mode == "home":
+        model = HomeRoutedPairwise(eng, rank, world, U, I, D, Bsz, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
     else:
         model = ShardedPairwise(eng, rank, world, U, I, D, kind=0, opt_kind=N.ORX_OPT_ADAGRAD, lr=B.LR, seed=1)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
@@ -312,7 +451,7 @@ def bench(args, rank, world, eng, barrier):
     if hasattr(model, "check"):
         model.check()
     # NVLink-bound exchange: bytes per GPU per direction per step
-    link_bytes = 2.0 * (world - 1) / world * (3 * D + 2) * 4 * Bsz
+    link_bytes = 2.0 * (world - 1) / world * ((2 if mode == "home" else 3) * (D + 1)) * 4 * Bsz
     nvlink_peak = 770.0
     roofline = {"bound": "nvlink", "achieved": link_bytes / (seconds / K) / 1e9, "peak": nvlink_peak, "unit": "GB/s",
                 "frac": link_bytes / (seconds / K) / 1e9 / nvlink_peak, "traffic": None,
@@ -326,7 +465,7 @@ def bench(args, rank, world, eng, barrier):
             "e2e_api": f"openrec_b200.{type(model).__module__.split('.')[-1]}.{type(model).__name__}.step"
                        "; pinned host ids in, global loss to host each step",
             "extra": {"last_loss": [float(x) for x in last], "total_items": I, "total_users": U,
-                      "exchange": {"peer": "NVLink peer loads/stores inside liborx kernels (CUDA IPC), 2 barriers/step",
-                                   "mailbox": "liborx kernels storing ids / rows / gradient rows into the peers' IPC-mapped "
-                                              "mailboxes over NVLink, 3 device-side flag barriers, no host sync",
+                      "exchange": {"home": "home-routed: triplets computed on the user row's owner; item rows / gradient rows "
+                                           "as peer stores into IPC-mapped mailboxes over NVLink, flag words instead of "
+                                           "barriers, no collective, no host sync",
                                    }.get(mode, "NCCL all-to-all (counts, ids, rows, gradient rows)")}}

@@ -42,22 +42,28 @@ def ids_any(x):
 
 
 class _OutRing:
-    """Pinned float[4] result buffers + events, recycled; a buffer still owned by an unread step node is
-    resolved (event wait + copy to python floats) before reuse."""
+    """Pinned float[4] result buffers + events, recycled.  A slot also keeps the step's pinned HOST id tensors alive:
+    orx_pairwise_step_host only enqueues the upload (on liborx's side stream), so the buffers must not go back to
+    torch's host allocator before the step's event has completed -- a later ``pin_memory()`` could otherwise be handed
+    the same block and overwrite ids that the GPU has not read yet.  A slot is reused only after its event is done."""
 
     def __init__(self, n=32):
         self.bufs = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(n)]
         self.events = [torch.cuda.Event() for _ in range(n)]
         self.owner = [None] * n
+        self.keep = [None] * n
+        self.used = [False] * n
         self.i = 0
 
-    def take(self, node):
+    def take(self, node, keep=None):
         k = self.i
         self.i = (k + 1) % len(self.bufs)
         old = self.owner[k]
         if old is not None and old.out_host is self.bufs[k]:
-            old.host_values()
-        self.owner[k] = node
+            old.host_values()                    # waits for that step's event and copies the floats out
+        elif self.used[k]:
+            self.events[k].synchronize()         # the step that used this slot (and its id upload) has finished
+        self.owner[k], self.keep[k], self.used[k] = node, keep, True
         return self.bufs[k], self.events[k]
 
 
@@ -65,15 +71,24 @@ class FusedRecommender(Model):
     """Base: subclasses define the kernels behind _orx_forward / _orx_run_step / _orx_run_grad."""
 
     def _tables(self, optimizer=None):
-        """orx_table_t structs of (user, item, bias); cached per optimizer (pointers never change)."""
+        """orx_table_t structs of (user, item, bias) for ``optimizer`` (None: no slots).  Cached per optimizer OBJECT:
+        the entry holds a weak reference to it (an id() can be reused by a new optimizer) and strong references to
+        the slot tensors whose raw pointers sit in the structs."""
         cache = self.__dict__.setdefault("_orx_cache_tables", {})
         key = id(optimizer)
-        t = cache.get(key)
-        if t is None:
-            vs = (self.user_latent_factor.embeddings, self.item_latent_factor.embeddings, self.item_bias.embeddings)
-            t = cache[key] = tuple(N.table(v.t) for v in vs) if optimizer is None else \
-                tuple(optimizer.table(v) for v in vs)
-        return t
+        ent = cache.get(key)
+        if ent is not None and (optimizer is None or ent[1]() is optimizer):
+            return ent[0]
+        vs = (self.user_latent_factor.embeddings, self.item_latent_factor.embeddings, self.item_bias.embeddings)
+        if optimizer is None:
+            ent = (tuple(N.table(v.t) for v in vs), None, None)
+        else:
+            import weakref
+            ent = (tuple(optimizer.table(v) for v in vs), weakref.ref(optimizer), [optimizer.slots(v) for v in vs])
+            for k in [k for k, e in cache.items() if e[1] is not None and e[1]() is None]:
+                del cache[k]                     # entries of optimizers that are gone
+        cache[key] = ent
+        return ent[0]
 
     def _orx_step_variables(self):
         return self.trainable_variables

@@ -44,7 +44,7 @@ class BPR(FusedRecommender):
     def _orx_run_step_host(self, node, optimizer, c_loss, c_l2):
         """ids in pinned host memory -> orx_pairwise_step_host: H2D, the three kernels and the D2H of
         (loss, l2_loss) are one C call's worth of stream work; the result lands in a pinned buffer."""
-        buf, ev = self._out_ring().take(node)
+        buf, ev = self._out_ring().take(node, keep=node.host_ids)
         N.engine().pairwise_step_host(self._kind, *self._tables(optimizer), *node.host_ids, optimizer.opt_struct(),
                                       buf, self._get_margin(), c_loss, c_l2)
         ev.record()

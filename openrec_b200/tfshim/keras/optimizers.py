@@ -34,11 +34,17 @@ class Optimizer:
 
     # slot tensors are created on first use (Keras creates them at first apply)
     def slots(self, var: Variable):
-        s = self._slots.get(id(var))
-        if s is None:
+        ent = self._slots.get(id(var))
+        if ent is None or ent[0]() is not var:      # id() of a dead variable can be reused: check the object itself
+            import weakref
             s = tuple(self._init_slot(var, k) for k in range(self._n_slots)) + (None,) * (2 - self._n_slots)
-            self._slots[id(var)] = s
-        return s
+            ent = self._slots[id(var)] = (weakref.ref(var), s)
+        return ent[1]
+
+    def slots_if_any(self, var: Variable):
+        """The slot tensors of ``var`` if they exist already (checkpoint save), else ()."""
+        ent = self._slots.get(id(var))
+        return ent[1] if ent is not None and ent[0]() is var else ()
 
     def _init_slot(self, var, k):
         return torch.zeros_like(var.t)

@@ -1,4 +1,5 @@
-"""Worker of tests/test_sharded_gloo.py: one rank of a world_size-R gloo job on CPU."""
+"""Worker of tests/test_sharded_gloo.py (CPU, gloo, oracle-backed engine) and tests/test_gpu_sharded.py (one process per
+GPU, the real kernels): one rank of a world_size-R job running three steps of the row-sharded pairwise step."""
 import os
 import sys
 
@@ -16,9 +17,8 @@ def main():
     out_path, kind, opt_kind = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     mode = sys.argv[4] if len(sys.argv) > 4 else "cpu"
     on_gpu = mode != "cpu"
-    peer = mode == "peer"
-    from openrec_b200.sharded import MailboxShardedPairwise, ShardedPairwise
-    if on_gpu:   # the real kernels, one process per GPU over NCCL
+    from openrec_b200.sharded import HomeRoutedPairwise, ShardedPairwise
+    if on_gpu:   # the real kernels, one process per GPU
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
         from openrec_b200 import native
@@ -32,13 +32,9 @@ def main():
     U, I, D, B = (61, 83, 16, 40) if not on_gpu else (1501, 2003, 128, 1024)
     sc = 0.05 if kind == 0 else 0.4
     user, item, bias = (rng.uniform(-sc, sc, s).astype(np.float32) for s in ((U, D), (I, D), (I, 1)))
-    if peer:   # one-sided NVLink peer-memory step
-        from openrec_b200.sharded_peer import PeerShardedPairwise
-        m = PeerShardedPairwise(engine, rank, world, U, I, D, B, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
-    elif mode.startswith("mailbox"):   # peer-store mailboxes; "mailbox-nccl": NCCL all-reduce as the barrier
-        m = MailboxShardedPairwise(engine, rank, world, U, I, D, B, kind=kind, opt_kind=opt_kind, lr=0.05, init=False,
-                                   barrier="nccl" if mode.endswith("nccl") else "flag")
-    else:
+    if mode == "home":   # peer-store mailboxes, home-routed (csrc/orx_shard.cu)
+        m = HomeRoutedPairwise(engine, rank, world, U, I, D, B, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
+    else:                # NCCL / gloo all-to-all form
         m = ShardedPairwise(engine, rank, world, U, I, D, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
     m.load_global(user, item, bias)
     losses = []

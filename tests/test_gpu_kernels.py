@@ -189,6 +189,95 @@ def test_pairwise_step_host_buffers(eng):
     close(tu, user), close(ti, item), close(tb, bias), close(ai, st["item"][0])
 
 
+def _adagrad_problem(rng, U, I, D):
+    user, item, bias = (rng.uniform(-0.05, 0.05, s).astype(np.float32) for s in ((U, D), (I, D), (I, 1)))
+    tabs = [dev(a) for a in (user, item, bias)]
+    accs = [torch.full_like(t, 0.1) for t in tabs]
+    ref = [a.astype(np.float64) for a in (user, item, bias)]
+    st = {k: (np.full_like(v, 0.1), None) for k, v in zip(("user", "item", "bias"), ref)}
+    return tabs, accs, ref, st
+
+
+def test_pairwise_step_host_runs_ahead(eng):
+    """Eight host-buffer steps enqueued back to back (no sync in between): the id upload and the index build of step t
+    run on the side stream under step t-1; staging buffers and index sets alternate and must not be reused early."""
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(16)
+    U, I, D, B = 700, 900, 128, 4096            # few rows: most lookups are duplicates (staging + tail every step)
+    tabs, accs, ref, st = _adagrad_problem(rng, U, I, D)
+    tt = [N.table(t, a) for t, a in zip(tabs, accs)]
+    ids = [[rng.integers(0, n, B).astype(np.int32) for n in (U, I, I)] for _ in range(8)]
+    pinned = [[torch.from_numpy(x).pin_memory() for x in b] for b in ids]
+    outs = [torch.zeros(4).pin_memory() for _ in range(8)]
+    for k in range(8):
+        eng.pairwise_step_host(N.ORX_PAIR_BPR, *tt, *pinned[k], N.opt(1, 0.05), outs[k])
+    torch.cuda.synchronize()
+    for k in range(8):
+        loss, l2 = O.pairwise_train_step("bpr", *ref, *ids[k], 1, st, k + 1, 0.05)
+        np.testing.assert_allclose(outs[k][0].item(), loss, rtol=2e-5)
+        np.testing.assert_allclose(outs[k][1].item(), l2, rtol=2e-5)
+    for t, r in zip(tabs, ref):
+        close(t, r)
+    close(accs[1], st["item"][0])
+
+
+def test_pairwise_prefetch_pipeline(eng):
+    """orx_pairwise_prefetch: the index of batch i+1 is built on the side stream while step i runs; a prefetch nobody
+    consumes (different ids) is dropped; results equal the plain sequence of steps."""
+    from openrec_b200 import native as N
+    rng = np.random.default_rng(17)
+    U, I, D, B = 600, 800, 128, 2048
+    tabs, accs, ref, st = _adagrad_problem(rng, U, I, D)
+    tt = [N.table(t, a) for t, a in zip(tabs, accs)]
+    ids = [[rng.integers(0, n, B).astype(np.int32) for n in (U, I, I)] for _ in range(6)]
+    dids = [[dev(x, torch.int32) for x in b] for b in ids]
+    out4 = torch.zeros(6, 4, device="cuda")
+    o = N.opt(1, 0.05)
+    torch.cuda.synchronize()                         # the id tensors are complete: ids_ready=True below is honest
+    eng.pairwise_prefetch(tt[0], tt[1], *dids[0], 1, ids_ready=True)
+    for k in range(6):
+        eng.pairwise_step(N.ORX_PAIR_BPR, *tt, *dids[k], o, out4[k])      # consumes the index prefetched for batch k
+        nxt = dids[(k + 1) % 6] if k != 2 else dids[0]                    # k == 2: nobody consumes this one -> dropped
+        eng.pairwise_prefetch(tt[0], tt[1], *nxt, 1, ids_ready=(k % 2 == 0))
+    torch.cuda.synchronize()
+    got = out4.cpu().numpy()
+    for k in range(6):
+        loss, l2 = O.pairwise_train_step("bpr", *ref, *ids[k], 1, st, k + 1, 0.05)
+        np.testing.assert_allclose(got[k, 0], loss, rtol=2e-5)
+        np.testing.assert_allclose(got[k, 1], l2, rtol=2e-5)
+    for t, r in zip(tabs, ref):
+        close(t, r)
+    # the dangling prefetch is dropped by the next call that builds its own index; a pointwise / sparse step still works
+    eng.pairwise_step(N.ORX_PAIR_UCML, *tt, *dids[3], o, out4[0])
+    torch.cuda.synchronize()
+
+
+def test_epoch_wrap():
+    """The batch-index epoch has 31 bits: starting just below 2^31 the counter wraps, the hash tables are emptied and
+    duplicates are still detected (a stale epoch compare would turn every step into hogwild updates)."""
+    from openrec_b200 import native as N
+    e = N.Engine(0)
+    try:
+        rng = np.random.default_rng(18)
+        U, I, D, B = 50, 70, 64, 512               # every row is hit many times
+        tabs, accs, ref, st = _adagrad_problem(rng, U, I, D)
+        tt = [N.table(t, a) for t, a in zip(tabs, accs)]
+        out4 = torch.zeros(4, device="cuda")
+        ids0 = [rng.integers(0, n, B).astype(np.int32) for n in (U, I, I)]
+        e.pairwise_step(N.ORX_PAIR_BPR, *tt, *[dev(x, torch.int32) for x in ids0], N.opt(1, 0.05), out4)   # allocates
+        O.pairwise_train_step("bpr", *ref, *ids0, 1, st, 1, 0.05)
+        e.debug_set_epoch(2 ** 31 - 3)
+        for k in range(5):                           # epochs 2^31-2, 2^31-1, wrap -> 1, 2, 3
+            ids = [rng.integers(0, n, B).astype(np.int32) for n in (U, I, I)]
+            e.pairwise_step(N.ORX_PAIR_BPR, *tt, *[dev(x, torch.int32) for x in ids], N.opt(1, 0.05), out4)
+            loss, l2 = O.pairwise_train_step("bpr", *ref, *ids, 1, st, k + 2, 0.05)
+            np.testing.assert_allclose(out4[0].item(), loss, rtol=2e-5)
+        for t, r in zip(tabs, ref):
+            close(t, r)
+    finally:
+        e.close()
+
+
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind", ["gmf", "wrmf"])
 def test_pointwise_golden_fwd_grad(eng, golden_dir, kind):

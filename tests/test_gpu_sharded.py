@@ -14,8 +14,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-# NCCL all-to-all path / peer-store mailboxes (flag barrier, NCCL barrier) / one-sided peer-load path
-@pytest.mark.parametrize("mode", ["gpu", "mailbox", "mailbox-nccl", "peer"])
+# NCCL all-to-all form / home-routed peer-store mailboxes (the 1-GPU form of the latter: test_gpu_shard_loopback.py)
+@pytest.mark.parametrize("mode", ["gpu", "home"])
 @pytest.mark.parametrize("kind,opt_kind", [(0, 1), (0, 0), (1, 1)])
 def test_sharded_step_on_gpus(tmp_path, kind, opt_kind, mode):
     world = min(torch.cuda.device_count(), 4)
