@@ -80,12 +80,13 @@ ORX_API int orx_stream_synchronize(orx_handle_t h, orx_stream_t stream);
 /* Test hook: place the handle's batch-index epoch counter (31 bits; the wrap path empties the hash tables). */
 ORX_API int orx_debug_set_epoch(orx_handle_t h, uint32_t epoch);
 
-/* Measurement hook (bench.py's roofline): while enabled, every *_step call records CUDA events on its
- * launch stream around its kernels -- [0] batch index build, [1] the fused gather-score-update kernel,
- * [2] tail (+ Adam sweep).  orx_profile_read waits for the recorded events, returns the summed device
- * time per phase (ms) and the number of steps recorded since the last read, and resets the counters. */
+/* Measurement hook (bench.py's roofline): while enabled, every 8th *_step call records CUDA events on its launch stream
+ * around its launches -- pairwise / pointwise steps: [0] batch index (or the wait for a prefetched one), [1] the fused
+ * gather-score-update kernel, [2] tail (+ Adam sweep); orx_shard_step: its six launches [0..5].  orx_profile_read waits
+ * for the recorded events, returns the summed device time of the first n_phases phases (ms) and the number of steps
+ * recorded since the last read, and resets the counter. */
 ORX_API int orx_profile_enable(orx_handle_t h, int32_t on);
-ORX_API int orx_profile_read(orx_handle_t h, float* ms3_host, int32_t* n_steps_host);
+ORX_API int orx_profile_read(orx_handle_t h, float* ms_host, int32_t n_phases, int32_t* n_steps_host);
 
 /* ---- LatentFactor ---------------------------------------------------------------------- */
 /* LatentFactor.__init__ 'uniform' initializer = U(-0.05,0.05), on device, counter-based RNG
@@ -207,9 +208,9 @@ ORX_API int orx_pairwise_grad_rows(orx_handle_t h, int32_t kind, const float* ro
  *   gin float[gin_cap][dim], ginb float[gin_cap]     gradient rows + bias gradients for rows I own
  *   meta int32[world][16]  per-peer counts / offsets / loss partials      flags int32[4*64+1] phase epochs + sticky error
  * orx_shard_sizes: element counts (4-byte words) of the eight mailboxes, in the order above.
- * orx_shard_step: the whole step in ONE call: seven launches on `s`, cross-rank ordering by flag words in peer memory
+ * orx_shard_step: the whole step in ONE call: six launches on `s`, cross-rank ordering by flag words in peer memory
  *   (no barrier launches, no collective, nothing returns to the host).  user/item/item_bias are this rank's LOCAL shards.
- *   epoch: strictly increasing per step, starting at 1.  phase_lo..phase_hi (0..6) selects a sub-range of the launches so
+ *   epoch: strictly increasing per step, starting at 1.  phase_lo..phase_hi (0..5) selects a sub-range of the launches so
  *   that several virtual ranks can be stepped phase by phase on one device (the 1-GPU loopback test).
  *   out4 = { loss, l2_loss (GLOBAL batch, identical on every rank), skipped triplets of this rank, staged rows }.
  *   The sticky error word flags[4*64] is 0 or: 1 a peer never arrived within timeout_ms, 2 more triplets routed to this

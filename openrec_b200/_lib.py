@@ -50,7 +50,7 @@ SIGNATURES = {
     "orx_stream_synchronize": [_vp, _vp],
     "orx_debug_set_epoch": [_vp, C.c_uint32],
     "orx_profile_enable": [_vp, _i32],
-    "orx_profile_read": [_vp, C.POINTER(C.c_float), C.POINTER(_i32)],
+    "orx_profile_read": [_vp, C.POINTER(C.c_float), _i32, C.POINTER(_i32)],
     "orx_fill_uniform": [_vp, _vp, _i64, _f, _f, _u64, _vp],
     "orx_gather": [_vp, _vp, _i64, _i32, _vp, _i32, _i64, _vp, _vp, _vp],
     "orx_censor": [_vp, _vp, _i64, _i32, _vp, _i32, _f, _vp],

@@ -66,7 +66,7 @@ struct orx_ctx {
   // measurement hook (orx_profile_*)
   int prof_on, prof_n, prof_cap;
   int prof_step;  // steps seen since orx_profile_enable: every 8th one carries the phase events
-  cudaEvent_t* prof_ev;  // [prof_cap*4]
+  cudaEvent_t* prof_ev;  // [prof_cap * ORX_PROF_EV]
   int32_t* bucket_cursor;  // owner-bucket scratch
   cudaStream_t side_stream;  // id upload + index build of the NEXT pairwise batch, beside the running step
   cudaEvent_t side_ev[2];
@@ -85,7 +85,8 @@ struct orx_ctx {
 int orx_next_epoch(orx_ctx* c, cudaStream_t st);
 void orx_shard_ws_release(orx_ctx* c);
 
-// record phase boundary k (0..3) of the current step on `st` when profiling is enabled
+#define ORX_PROF_EV 8   // event slots per sampled step: up to 7 phases (the sharded step has seven launches)
+// record phase boundary k (0..7) of the current step on `st` when profiling is enabled
 // Only every 8th step is instrumented: four timing-event records per step sit between the kernels of the step that is
 // being timed.  Suspected cost (not yet isolated): bench.py's un-instrumented UCML loop ran at 612 M/s against 555 M/s
 // for the instrumented BPR loop in r1w although both step kernels take 71 us under ncu.
@@ -93,7 +94,7 @@ static inline bool orx_prof_sampled(const orx_ctx* c) {
   return c->prof_on && (c->prof_step & 7) == 0 && c->prof_n < c->prof_cap;
 }
 static inline void orx_prof_mark(orx_ctx* c, int k, cudaStream_t st) {
-  if (orx_prof_sampled(c)) cudaEventRecord(c->prof_ev[c->prof_n * 4 + k], st);
+  if (orx_prof_sampled(c)) cudaEventRecord(c->prof_ev[c->prof_n * ORX_PROF_EV + k], st);
 }
 static inline void orx_prof_next(orx_ctx* c) {
   if (!c->prof_on) return;
@@ -116,6 +117,31 @@ struct OrxOptDev {
 #ifdef __CUDACC__
 
 #define ORX_FULL 0xffffffffu
+
+// Programmatic dependent launch (sm_90+): a kernel launched with orx_launch_pdl may become resident while its
+// predecessor on the stream is still draining; it must execute orx_pdl_wait() before it touches anything the predecessor
+// wrote (a no-op when launched normally).  The predecessor calls orx_pdl_trigger() once a block has finished its main
+// loop: the dependent grid is released when every block has triggered or exited, so launch latency and grid drain overlap.
+__device__ __forceinline__ void orx_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void orx_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool orx_pdl_enabled();   // ORX_PDL=0 turns the attribute off (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t orx_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = orx_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 __device__ __forceinline__ uint32_t orx_hash32(uint32_t id, int shift) { return (id * 2654435769u) >> shift; }
 

@@ -1,5 +1,6 @@
 // orx_ctx.cu -- context, workspace and error plumbing of liborx.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "orx_common.cuh"
@@ -14,6 +15,15 @@ void orx_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* orx_last_error_string(void) { return g_err; }
+
+bool orx_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ORX_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
 extern "C" int orx_abi_version(void) { return ORX_ABI_VERSION; }
 
 extern "C" int orx_device_count(int* n) {
@@ -204,7 +214,7 @@ extern "C" int orx_destroy(orx_handle_t h) {
     }
   }
   if (h->prof_ev) {
-    for (int i = 0; i < h->prof_cap * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
+    for (int i = 0; i < h->prof_cap * ORX_PROF_EV; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;
   }
   delete h;
@@ -215,9 +225,9 @@ extern "C" int orx_profile_enable(orx_handle_t h, int32_t on) {
   ORX_REQUIRE(h != nullptr, "null handle");
   ORX_CUDA(cudaSetDevice(h->device));
   if (on && !h->prof_ev) {
-    h->prof_cap = 4096;
-    h->prof_ev = new cudaEvent_t[h->prof_cap * 4];
-    for (int i = 0; i < h->prof_cap * 4; ++i) ORX_CUDA(cudaEventCreate(&h->prof_ev[i]));
+    h->prof_cap = 1024;
+    h->prof_ev = new cudaEvent_t[h->prof_cap * ORX_PROF_EV];
+    for (int i = 0; i < h->prof_cap * ORX_PROF_EV; ++i) ORX_CUDA(cudaEventCreate(&h->prof_ev[i]));
   }
   h->prof_on = on ? 1 : 0;
   h->prof_n = 0;
@@ -225,17 +235,17 @@ extern "C" int orx_profile_enable(orx_handle_t h, int32_t on) {
   return ORX_OK;
 }
 
-extern "C" int orx_profile_read(orx_handle_t h, float* ms3, int32_t* n_steps) {
-  ORX_REQUIRE(h != nullptr && ms3 && n_steps, "null pointer");
+extern "C" int orx_profile_read(orx_handle_t h, float* ms, int32_t n_phases, int32_t* n_steps) {
+  ORX_REQUIRE(h != nullptr && ms && n_steps && n_phases >= 1 && n_phases < ORX_PROF_EV, "bad arguments");
   ORX_CUDA(cudaSetDevice(h->device));
-  ms3[0] = ms3[1] = ms3[2] = 0.f;
+  for (int k = 0; k < n_phases; ++k) ms[k] = 0.f;
   *n_steps = h->prof_n;
   for (int i = 0; i < h->prof_n; ++i) {
-    ORX_CUDA(cudaEventSynchronize(h->prof_ev[i * 4 + 3]));
-    for (int k = 0; k < 3; ++k) {
-      float ms = 0.f;
-      ORX_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[i * 4 + k], h->prof_ev[i * 4 + k + 1]));
-      ms3[k] += ms;
+    ORX_CUDA(cudaEventSynchronize(h->prof_ev[i * ORX_PROF_EV + n_phases]));
+    for (int k = 0; k < n_phases; ++k) {
+      float t = 0.f;
+      ORX_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i * ORX_PROF_EV + k], h->prof_ev[i * ORX_PROF_EV + k + 1]));
+      ms[k] += t;
     }
   }
   h->prof_n = 0;

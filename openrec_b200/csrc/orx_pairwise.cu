@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
   const int grp = lane / G, gl = lane % G;
   const int t = warp * CH + lane;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  orx_pdl_wait();
 
   // ---- ids of triplet t (lanes < CH)
   int u_id = 0, p_id = 0, n_id = 0, du = -1, dp = -1, dn = -1, flags = 0;
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(256, MINB) k_pair_step(const PairArgs a) {
     }
   }
 
+  orx_pdl_trigger();
   // ---- item_bias: lane-parallel, one lane per triplet of the chunk
   if (flags & 1) {
     if (flags & 4) {
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(256) k_pair_step_generic(const PairArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int D = a.D;
   float loss_acc = 0.f, l2_acc = 0.f;
+  orx_pdl_wait();
   for (int j = 0; j < CH; ++j) {
     const int t = warp * CH + j;
     if (t >= a.B) break;
@@ -489,6 +492,7 @@ __global__ void __launch_bounds__(256) k_sparse_tail(const TailArgs a) {
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  orx_pdl_wait();
   const int nu = a.counters[0], ni = a.counters[1], nbad = a.counters[3];
   const int D = a.D;
   for (int r = gwarp; r < nu + ni; r += nwarps) {
@@ -596,10 +600,10 @@ __global__ void __launch_bounds__(256) k_sparse_tail(const TailArgs a) {
 int orx_launch_tail(orx_ctx* c, const TailArgs& ta, int opt_kind, cudaStream_t st) {
   const int grid = c->num_sms * 4;  // ~1-2 staged rows per warp: the tail is a latency chain, not bandwidth
   switch (opt_kind) {
-    case ORX_OPT_SGD: k_sparse_tail<ORX_OPT_SGD><<<grid, 256, 0, st>>>(ta); break;
-    case ORX_OPT_ADAGRAD: k_sparse_tail<ORX_OPT_ADAGRAD><<<grid, 256, 0, st>>>(ta); break;
-    case ORX_OPT_ADAM_LAZY: k_sparse_tail<ORX_OPT_ADAM_LAZY><<<grid, 256, 0, st>>>(ta); break;
-    default: k_sparse_tail<ORX_OPT_ADAM_DENSE><<<grid, 256, 0, st>>>(ta); break;
+    case ORX_OPT_SGD: orx_launch_pdl(k_sparse_tail<ORX_OPT_SGD>, dim3(grid), dim3(256), 0, st, ta); break;
+    case ORX_OPT_ADAGRAD: orx_launch_pdl(k_sparse_tail<ORX_OPT_ADAGRAD>, dim3(grid), dim3(256), 0, st, ta); break;
+    case ORX_OPT_ADAM_LAZY: orx_launch_pdl(k_sparse_tail<ORX_OPT_ADAM_LAZY>, dim3(grid), dim3(256), 0, st, ta); break;
+    default: orx_launch_pdl(k_sparse_tail<ORX_OPT_ADAM_DENSE>, dim3(grid), dim3(256), 0, st, ta); break;
   }
   ORX_LAUNCH_CHECK();
   return ORX_OK;
@@ -630,7 +634,7 @@ static int launch_pair_step_kind_opt(const PairArgs& pa, cudaStream_t st, int* n
     const int nw = (B + ch - 1) / ch;
     const int blocks = (nw + 7) / 8;
     *n_partials = blocks;
-    kern<<<blocks, 256, 0, st>>>(pa);
+    orx_launch_pdl(kern, dim3(blocks), dim3(256), 0, st, pa);
   };
   switch (pa.D) {
     case 32: go(k_pair_step<KIND, OPT, 32, 8, 2, !LAZY>, 8); break;

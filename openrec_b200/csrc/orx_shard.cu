@@ -8,7 +8,7 @@
 // 16-byte-aligned D-float row (512 B at D = 128) or of a coalesced run of 4-byte words into a small mailbox mapped
 // through CUDA IPC.  No collective, no host sync, no count ever visits the host.
 //
-// One step on rank `me` = seven launches on one stream; cross-rank ordering is by flag words in peer memory, written by
+// One step on rank `me` = six launches on one stream; cross-rank ordering is by flag words in peer memory, written by
 // the LAST block of the producing kernel (release, system scope) and polled by EVERY block of the consuming kernel
 // (acquire) -- there are no barrier launches:
 //
@@ -20,20 +20,20 @@
 //                          land contiguously: 8 rows = 4 KB + one 32 B run of biases), publish the gradient-inbox bases -> flag 2
 //   k_sh_compute  home   : [wait 2] score + loss + gradients per triplet; the USER row is updated right here (owned rows
 //                          in registers, duplicated rows through the staging buffer -- the single-GPU scheme); the two
-//                          item gradient rows are stored into their owners' `gin`; bias gradients are staged locally
-//   k_sh_finish   home   : bias-gradient runs -> owners' `ginb` (coalesced), staged user rows -> optimizer,
-//                          (loss, l2) partial of this rank -> every rank's meta                                        -> flag 3
+//                          item gradient rows (+ one 4-byte bias gradient each) are stored into their owners' `gin` /
+//                          `ginb`; the last block sends this rank's (loss, l2) partial to every rank                   -> flag 3
 //   k_sh_apply    owner  : [wait 3] rows requested once: optimizer straight from the gradient row; duplicated rows are
 //                          summed in the staging buffer
-//   k_sh_item_tail owner : staged item rows -> optimizer; out4 = GLOBAL (loss, l2_loss), identical on every rank
+//   k_sh_tail     both   : staged user and item rows -> optimizer; out4 = GLOBAL (loss, l2_loss), identical on every rank
 //
-// All gathers of a step read pre-step values: item rows are only written by k_sh_apply / k_sh_item_tail, which follow
+// All gathers of a step read pre-step values: item rows are only written by k_sh_apply / k_sh_tail, which follow
 // the rank's own k_sh_serve on the stream; user rows are read and written by the one triplet that owns them, shared ones
-// only in k_sh_finish.  Mailbox reuse across steps needs no extra synchronisation (proof per buffer in DESIGN.md 7).
+// only in k_sh_tail.  Mailbox reuse across steps needs no extra synchronisation (proof per buffer in DESIGN.md 7).
 //
-// phase_lo / phase_hi of orx_shard_step select a sub-range of the seven launches, so that R "virtual ranks" can share ONE
+// phase_lo / phase_hi of orx_shard_step select a sub-range of the six launches, so that R "virtual ranks" can share ONE
 // device and ONE stream (tests/test_gpu_shard_loopback.py): phase k is issued for every rank before phase k + 1, every
 // flag is already set when its consumer runs, and the exact kernels of the multi-GPU step are exercised on a 1-GPU box.
+#include <stdlib.h>
 #include <string.h>
 
 #include "orx_common.cuh"
@@ -50,7 +50,7 @@ enum { SH_M_TRIPS = 0,    // triplets r routed to X                             
        SH_M_REQS = 1,     // item rows home r requests from owner X                  (k_sh_request)
        SH_M_GOTOFF = 2,   // first row of r's `got` that owner X fills               (k_sh_request)
        SH_M_GINBASE = 3,  // first row of owner r's `gin` that home X fills, -1 = overflow (k_sh_serve)
-       SH_M_LOSS = 4, SH_M_L2 = 5 };   // r's partial sums, float bits                (k_sh_finish)
+       SH_M_LOSS = 4, SH_M_L2 = 5 };   // r's partial sums, float bits                (k_sh_compute)
 
 // local control words (ShardWs::ctl)
 enum { SH_C_CURH = 0, SH_C_CURO = SH_MAX_R, SH_C_GOFF = 2 * SH_MAX_R, SH_C_RCO = 3 * SH_MAX_R + 1,
@@ -79,7 +79,6 @@ struct ShardWs {       // per-handle local scratch
   int32_t* trip_u;     // [home_cap]      local user row of home triplet t
   int32_t* slot;       // [2 * home_cap]  (owner << 24 | index in my bucket for that owner) of lookup 2t + q, -1 = dropped
   int32_t* req;        // [gin_cap]       local item row requested as gradient-inbox row j (-1 = padding / invalid)
-  float* gbs;          // [got_rows]      bias gradients in `got` order
   int32_t* ctl;        // [SH_C_WORDS]
 };
 
@@ -92,6 +91,24 @@ __device__ __forceinline__ int sh_bucket_of(const int32_t* off, int R, int p) { 
     if (off[mid + 1] > p) hi = mid; else lo = mid + 1;
   }
   return lo;
+}
+
+// rank of this lane's key inside a shared-memory counter array, warp-aggregated: one atomicAdd per distinct key and warp
+// instruction instead of one per lane (with R = 2..8 owners every lane of a block hits the same few words, and
+// same-address shared atomics serialise: 20 us of a 64-block kernel in the first version, profiles/r2f).
+__device__ __forceinline__ int sh_rank_add(int32_t* cnt, int key, bool active) {
+  const unsigned act = __ballot_sync(ORX_FULL, active);
+  int rk = 0;
+  if (active) {
+    const unsigned peers = __match_any_sync(act, key);
+    const int leader = __ffs(peers) - 1;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cnt[key], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    rk = base + __popc(peers & ((1u << lane) - 1u));
+  }
+  return rk;
 }
 
 __device__ __forceinline__ unsigned long long sh_now() {
@@ -125,15 +142,19 @@ __device__ __forceinline__ void sh_wait(const ShardDev& x, int phase, int epoch)
 }
 
 // every block of a producer, at its very end: the last block publishes `epoch` for `phase` to every rank.
-// `publish(r)` (threads r < world of the last block) stores the producer's per-peer meta words first.
+// `publish()` (all threads of the last block) stores the producer's per-peer meta words first.
+// Ordering: each block orders its (peer) stores before its ticket with a GPU-scope fence; the last block, having observed
+// every ticket, issues the one SYSTEM-scope fence in front of the flag stores.  Fences are cumulative (PTX memory model:
+// causality order is transitive over morally-strong edges of different scopes), so a peer that acquires the flag sees
+// every block's stores.  A system fence per block cost ~5 us at the end of every launch (profiles/r2g).
 template <typename F>
 __device__ __forceinline__ void sh_arrive(const ShardDev& x, int32_t* done, int phase, int epoch, F publish) {
   __shared__ bool sh_last;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();                     // this block's peer stores are performed before its ticket
+    __threadfence();                            // this block's stores are ordered before its ticket (GPU scope)
     sh_last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
-    __threadfence_system();
+    __threadfence();
   }
   __syncthreads();
   if (!sh_last) return;
@@ -156,6 +177,7 @@ __global__ void __launch_bounds__(256) k_sh_route(ShardDev x, ShardWs w, const i
   __shared__ int32_t cnt[SH_MAX_R], base[SH_MAX_R];
   const int R = x.world;
   if ((int)threadIdx.x < R) cnt[threadIdx.x] = 0;
+  orx_pdl_wait();
   __syncthreads();
   int h[4], rk[4];
   int32_t uu[4], pp[4], nn[4];
@@ -163,17 +185,19 @@ __global__ void __launch_bounds__(256) k_sh_route(ShardDev x, ShardWs w, const i
   for (int k = 0; k < 4; ++k) {
     const int i = blockIdx.x * 1024 + k * 256 + threadIdx.x;
     h[k] = -1;
+    bool ok = false;
     if (i < B) {
       const int32_t u = uid[i], p = pid[i], n = nid[i];
       // a triplet with ANY id out of range is skipped as a whole, like the single-GPU step (orx_pairwise.cu)
-      if (u >= 0 && (int64_t)u < U && p >= 0 && (int64_t)p < I && n >= 0 && (int64_t)n < I) {
+      ok = u >= 0 && (int64_t)u < U && p >= 0 && (int64_t)p < I && n >= 0 && (int64_t)n < I;
+      if (ok) {
         h[k] = u % R;
-        rk[k] = atomicAdd(&cnt[h[k]], 1);
         uu[k] = u / R; pp[k] = p; nn[k] = n;
       } else {
         atomicAdd(w.ctl + SH_C_BAD, 1);
       }
     }
+    rk[k] = sh_rank_add(cnt, ok ? h[k] : 0, ok);
   }
   __syncthreads();
   if ((int)threadIdx.x < R) base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(w.ctl + SH_C_CURH + threadIdx.x, cnt[threadIdx.x]) : 0;
@@ -187,6 +211,7 @@ __global__ void __launch_bounds__(256) k_sh_route(ShardDev x, ShardWs w, const i
     box[x.batch_cap + idx] = pp[k];
     box[2 * x.batch_cap + idx] = nn[k];
   }
+  orx_pdl_trigger();
   sh_arrive(x, w.ctl + SH_C_DONE + 0, 0, epoch, [&]() {
     if ((int)threadIdx.x < R) {
       const int r = threadIdx.x;
@@ -203,6 +228,7 @@ __global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHa
   __shared__ int32_t toff[SH_MAX_R + 1], cnt[SH_MAX_R], base[SH_MAX_R], goff[SH_MAX_R + 1];
   __shared__ int T_sh;
   const int R = x.world, me = x.rank;
+  orx_pdl_wait();
   sh_wait(x, 0, epoch);
   if (threadIdx.x == 0) {
     const int32_t* m = x.meta[me];
@@ -228,18 +254,20 @@ __global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHa
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int t = c0 + k * 256 + threadIdx.x;
-      o[2 * k] = o[2 * k + 1] = -1;
+      o[2 * k] = o[2 * k + 1] = 0;
+      int32_t u = -1;
       if (t < T) {
         const int s = sh_bucket_of(toff, R, t);
         const int32_t* b = box + (int64_t)s * 3 * x.batch_cap + (t - toff[s]);
-        const int32_t u = __ldcg(b), p = __ldcg(b + x.batch_cap), n = __ldcg(b + 2 * x.batch_cap);
+        u = __ldcg(b);
+        const int32_t p = __ldcg(b + x.batch_cap), n = __ldcg(b + 2 * x.batch_cap);
         w.trip_u[t] = u;
-        orx_hash_insert(hu, u, 0);
         o[2 * k] = p % R; lid[2 * k] = p / R;
         o[2 * k + 1] = n % R; lid[2 * k + 1] = n / R;
-        rk[2 * k] = atomicAdd(&cnt[o[2 * k]], 1);
-        rk[2 * k + 1] = atomicAdd(&cnt[o[2 * k + 1]], 1);
       }
+      rk[2 * k] = sh_rank_add(cnt, o[2 * k], t < T);
+      rk[2 * k + 1] = sh_rank_add(cnt, o[2 * k + 1], t < T);
+      if (t < T) orx_hash_insert(hu, u, 0);
     }
     __syncthreads();
     if ((int)threadIdx.x < R) base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(w.ctl + SH_C_CURO + threadIdx.x, cnt[threadIdx.x]) : 0;
@@ -263,6 +291,7 @@ __global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHa
     }
     __syncthreads();
   }
+  orx_pdl_trigger();
   sh_arrive(x, w.ctl + SH_C_DONE + 1, 1, epoch, [&]() {
     if (threadIdx.x == 0) {
       int acc = 0;
@@ -296,6 +325,7 @@ __global__ void __launch_bounds__(256) k_sh_serve(ShardDev x, ShardWs w, const f
   __shared__ int32_t rc[SH_MAX_R], goff[SH_MAX_R], gbase[SH_MAX_R + 1];
   __shared__ int total_sh;
   const int R = x.world, me = x.rank, D = x.D, nq = D >> 2;
+  orx_pdl_wait();
   sh_wait(x, 1, epoch);
   if (threadIdx.x == 0) {
     const int32_t* m = x.meta[me];
@@ -342,22 +372,25 @@ __global__ void __launch_bounds__(256) k_sh_serve(ShardDev x, ShardWs w, const f
       valid = idx0 + lane < rc[h];
       int32_t id = valid ? __ldcg(box + (int64_t)h * x.req_cap + idx0 + lane) : -1;
       if (id < 0 || (int64_t)id >= rows) id = -1;
-      w.req[j0 + lane] = id;
-      if (id >= 0) orx_hash_insert(hi, id, 0);
-      if (valid) x.gotb[h][goff[h] + idx0 + lane] = id >= 0 ? __ldcg(ibias + id) : 0.f;
       my_id = id;
     }
     const unsigned vmask = __ballot_sync(ORX_FULL, valid) & 0xffu;
     float* dst0 = x.got[h] + (int64_t)(goff[h] + idx0) * D;
     float4 v[8][NQ];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 8; ++k) {     // all eight rows in flight before anything that stalls (the index inserts below)
       const int32_t id = __shfl_sync(ORX_FULL, my_id, k);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int e = q * 32 + lane;
         v[k][q] = (id >= 0 && e < nq) ? __ldcg(reinterpret_cast<const float4*>(item + (int64_t)id * D) + e) : z4;
       }
+    }
+    if (lane < 8) {
+      w.req[j0 + lane] = my_id;
+      const float b = my_id >= 0 ? __ldcg(ibias + my_id) : 0.f;
+      if (my_id >= 0) orx_hash_insert(hi, my_id, 0);
+      if (valid) x.gotb[h][goff[h] + idx0 + lane] = b;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -369,6 +402,7 @@ __global__ void __launch_bounds__(256) k_sh_serve(ShardDev x, ShardWs w, const f
       }
     }
   }
+  orx_pdl_trigger();
   sh_arrive(x, w.ctl + SH_C_DONE + 2, 2, epoch, [&]() {});
 }
 
@@ -379,7 +413,7 @@ struct ShCompArgs {
   float *U, *Us0, *Us1;     // local user shard + slots
   OrxHash hu;
   float* gu;                // user staging [.., D]
-  float margin, c_loss, c_l2, inv_B;
+  float margin, c_loss, c_l2, inv_B, loss_scale;
   OrxOptDev opt;
   float* partials;          // [2 * warps of the grid]
 };
@@ -389,12 +423,12 @@ __global__ void __launch_bounds__(256) k_sh_compute(ShardDev x, ShardWs w, ShCom
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   constexpr int TPW = NQ == 1 ? 4 : (NQ == 2 ? 2 : 1);     // triplets in flight per warp
-  __shared__ int32_t goff[SH_MAX_R], gbase[SH_MAX_R], rco[SH_MAX_R];
+  __shared__ int32_t goff[SH_MAX_R], gbase[SH_MAX_R];
   const int R = x.world, me = x.rank, D = x.D, nq = D >> 2;
+  orx_pdl_wait();
   sh_wait(x, 2, epoch);
   if ((int)threadIdx.x < R) {
     goff[threadIdx.x] = w.ctl[SH_C_GOFF + threadIdx.x];
-    rco[threadIdx.x] = w.ctl[SH_C_RCO + threadIdx.x];
     gbase[threadIdx.x] = __ldcg(x.meta[me] + SH_META * threadIdx.x + SH_M_GINBASE);
   }
   __syncthreads();
@@ -412,6 +446,8 @@ __global__ void __launch_bounds__(256) k_sh_compute(ShardDev x, ShardWs w, ShCom
     int my_u = -1, my_du = -1, my_own = 0, my_pp = 0, my_pn = 0;
     float* my_dp = nullptr;
     float* my_dn = nullptr;
+    float* my_bdp = nullptr;
+    float* my_bdn = nullptr;
     float my_bp = 0.f, my_bn = 0.f;
     if (lane < TPW && t0 + lane < T) {
       const int t = t0 + lane;
@@ -422,8 +458,14 @@ __global__ void __launch_bounds__(256) k_sh_compute(ShardDev x, ShardWs w, ShCom
         const int on = sn >> SH_IDX_BITS, in = sn & ((1 << SH_IDX_BITS) - 1);
         my_pp = goff[op] + ip;
         my_pn = goff[on] + in;
-        if (gbase[op] >= 0 && gbase[op] + ip < x.gin_cap) my_dp = x.gin[op] + (int64_t)(gbase[op] + ip) * D;
-        if (gbase[on] >= 0 && gbase[on] + in < x.gin_cap) my_dn = x.gin[on] + (int64_t)(gbase[on] + in) * D;
+        if (gbase[op] >= 0 && gbase[op] + ip < x.gin_cap) {
+          my_dp = x.gin[op] + (int64_t)(gbase[op] + ip) * D;
+          my_bdp = x.ginb[op] + gbase[op] + ip;
+        }
+        if (gbase[on] >= 0 && gbase[on] + in < x.gin_cap) {
+          my_dn = x.gin[on] + (int64_t)(gbase[on] + in) * D;
+          my_bdn = x.ginb[on] + gbase[on] + in;
+        }
         my_bp = __ldcg(gotb + my_pp);
         my_bn = __ldcg(gotb + my_pn);
         my_own = orx_hash_find(a.hu, my_u, &my_du) == 1u;
@@ -491,84 +533,49 @@ __global__ void __launch_bounds__(256) k_sh_compute(ShardDev x, ShardWs w, ShCom
           orx_red4(a.gu + (int64_t)du * D + 4 * e, gu);
         }
       }
-      if (lane == 0) {          // bias gradient of the positive item: BPR +g, UCML -g; the negative gets the opposite sign
+      {                         // bias gradient of the positive item: BPR +g, UCML -g; the negative gets the opposite sign
+        float* bdp = reinterpret_cast<float*>(__shfl_sync(ORX_FULL, (unsigned long long)my_bdp, k));
+        float* bdn = reinterpret_cast<float*>(__shfl_sync(ORX_FULL, (unsigned long long)my_bdn, k));
         const float gb = (KIND == ORX_PAIR_BPR) ? g : -g;
-        w.gbs[pp] = gb;
-        w.gbs[pn] = -gb;
+        if (lane == 0) {        // one 4-byte peer store each, at the inbox row of the gradient row
+          if (bdp) *bdp = gb;
+          if (bdn) *bdn = -gb;
+        }
       }
     }
   }
+  orx_pdl_trigger();
   loss_acc = orx_group_sum<32>(loss_acc);
   l2_acc = orx_group_sum<32>(l2_acc);
   if (lane == 0) {
     a.partials[2 * gwarp] = loss_acc;
     a.partials[2 * gwarp + 1] = l2_acc;
   }
-}
-
-// bias-gradient runs -> owners, staged user rows -> optimizer, my (loss, l2) partial -> every rank; then flag 3
-template <int OPT>
-__global__ void __launch_bounds__(256) k_sh_finish(ShardDev x, ShardWs w, ShCompArgs a, int n_partials, float loss_scale,
-                                                   int32_t* counters, int epoch) {
-  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
-  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
-  __shared__ int32_t goff[SH_MAX_R + 1], gbase[SH_MAX_R], rco[SH_MAX_R];
-  __shared__ double sh[2][256];
-  const int R = x.world, me = x.rank, D = x.D;
-  if ((int)threadIdx.x <= R) goff[threadIdx.x] = w.ctl[SH_C_GOFF + threadIdx.x];
-  if ((int)threadIdx.x < R) {
-    rco[threadIdx.x] = w.ctl[SH_C_RCO + threadIdx.x];
-    gbase[threadIdx.x] = __ldcg(x.meta[me] + SH_META * threadIdx.x + SH_M_GINBASE);
-  }
-  __syncthreads();
-  const int span = goff[R];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < span; i += gridDim.x * blockDim.x) {
-    const int o = sh_bucket_of(goff, R, i);
-    const int e = i - goff[o];
-    if (e < rco[o] && gbase[o] >= 0 && gbase[o] + e < x.gin_cap) x.ginb[o][gbase[o] + e] = w.gbs[i];
-  }
-  // staged (duplicated) user rows: once per unique row, staging re-zeroed
-  const int lane = threadIdx.x & 31;
-  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  const int nu = counters[0];
-  for (int r = gwarp; r < nu; r += nw) {
-    const int id = a.hu.did[r];
-    for (int e = lane * 4; e < D; e += 128) {
-      const int64_t off = (int64_t)id * D + e;
-      float4* gp = reinterpret_cast<float4*>(a.gu + (int64_t)r * D + e);
-      const float4 g = __ldcg(gp);
-      float4 wv = __ldcg(reinterpret_cast<const float4*>(a.U + off));
-      float4 s0v = S0 ? __ldcg(reinterpret_cast<const float4*>(a.Us0 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 s1v = S1 ? __ldcg(reinterpret_cast<const float4*>(a.Us1 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      __stcg(reinterpret_cast<float4*>(a.U + off), orx_apply4<OPT>(wv, g, s0v, s1v, a.opt));
-      if (S0) __stcg(reinterpret_cast<float4*>(a.Us0 + off), s0v);
-      if (S1) __stcg(reinterpret_cast<float4*>(a.Us1 + off), s1v);
-      __stcg(gp, make_float4(0.f, 0.f, 0.f, 0.f));
+  // The LAST block to finish reduces this rank's (loss, l2) partials, sends the pair to every rank and releases flag 3.
+  __shared__ double sh_red[2][256];
+  sh_arrive(x, w.ctl + SH_C_DONE + 3, 3, epoch, [&]() {
+    double l = 0.0, q = 0.0;                           // deterministic (fixed order, double) reduction of my partials
+    const int np = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+      l += (double)__ldcg(a.partials + 2 * i);
+      q += (double)__ldcg(a.partials + 2 * i + 1);
     }
-  }
-  if (blockIdx.x == 0) {      // deterministic (fixed order, double) reduction of this rank's partials
-    double l = 0.0, q = 0.0;
-    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) {
-      l += (double)a.partials[2 * i];
-      q += (double)a.partials[2 * i + 1];
-    }
-    sh[0][threadIdx.x] = l;
-    sh[1][threadIdx.x] = q;
+    sh_red[0][threadIdx.x] = l;
+    sh_red[1][threadIdx.x] = q;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
       if ((int)threadIdx.x < s) {
-        sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
-        sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+        sh_red[0][threadIdx.x] += sh_red[0][threadIdx.x + s];
+        sh_red[1][threadIdx.x] += sh_red[1][threadIdx.x + s];
       }
       __syncthreads();
     }
     if ((int)threadIdx.x < R) {
       int32_t* m = x.meta[threadIdx.x] + SH_META * me;
-      m[SH_M_LOSS] = __float_as_int((float)(sh[0][0] * (double)loss_scale));
-      m[SH_M_L2] = __float_as_int((float)(0.5 * sh[1][0]));
+      m[SH_M_LOSS] = __float_as_int((float)(sh_red[0][0] * (double)a.loss_scale));
+      m[SH_M_L2] = __float_as_int((float)(0.5 * sh_red[1][0]));
     }
-  }
-  sh_arrive(x, w.ctl + SH_C_DONE + 3, 3, epoch, [&]() {});
+  });
 }
 
 // ---------------------------------------------------------------------------------------
@@ -588,6 +595,7 @@ __global__ void __launch_bounds__(256) k_sh_apply(ShardDev x, ShardWs w, ShApply
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   constexpr int GRP = NQ == 1 ? 4 : (NQ == 2 ? 2 : 1);   // rows whose loads are issued together
   const int me = x.rank, D = x.D, nq = D >> 2;
+  orx_pdl_wait();
   sh_wait(x, 3, epoch);
   const int n = w.ctl[SH_C_NREQ];
   const int lane = threadIdx.x & 31;
@@ -653,37 +661,71 @@ __global__ void __launch_bounds__(256) k_sh_apply(ShardDev x, ShardWs w, ShApply
       }
     }
   }
+  orx_pdl_trigger();
 }
 
-// staged (duplicated) item rows -> optimizer; global (loss, l2) from the meta mailbox; counters reset
+// staged (duplicated) user and item rows -> optimizer, once per unique row, staging re-zeroed; global (loss, l2) from the
+// meta mailbox; counters reset.  Two rows per warp iteration so that both rows' loads are in flight together.
+struct ShTailArgs {
+  float *U, *Us0, *Us1;
+  OrxHash hu;
+  float* gu;
+};
+
 template <int OPT>
-__global__ void __launch_bounds__(256) k_sh_item_tail(ShardDev x, ShardWs w, ShApplyArgs a, int32_t* counters, float* out4) {
+__device__ __forceinline__ void sh_apply_staged2(float* W, float* P0, float* P1, float* G, int D, int lane, int id1, int r1,
+                                                 bool two, int id2, int r2, const OrxOptDev& opt) {
+  constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
+  constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = lane * 4; e < D; e += 128) {
+    const int64_t o1 = (int64_t)id1 * D + e, o2 = (int64_t)id2 * D + e;
+    float4* gp1 = reinterpret_cast<float4*>(G + (int64_t)r1 * D + e);
+    float4* gp2 = reinterpret_cast<float4*>(G + (int64_t)r2 * D + e);
+    const float4 g1 = __ldcg(gp1), g2 = two ? __ldcg(gp2) : z;
+    float4 w1 = __ldcg(reinterpret_cast<const float4*>(W + o1)), w2 = two ? __ldcg(reinterpret_cast<const float4*>(W + o2)) : z;
+    float4 p1 = S0 ? __ldcg(reinterpret_cast<const float4*>(P0 + o1)) : z, p2 = (S0 && two) ? __ldcg(reinterpret_cast<const float4*>(P0 + o2)) : z;
+    float4 q1 = S1 ? __ldcg(reinterpret_cast<const float4*>(P1 + o1)) : z, q2 = (S1 && two) ? __ldcg(reinterpret_cast<const float4*>(P1 + o2)) : z;
+    __stcg(reinterpret_cast<float4*>(W + o1), orx_apply4<OPT>(w1, g1, p1, q1, opt));
+    if (S0) __stcg(reinterpret_cast<float4*>(P0 + o1), p1);
+    if (S1) __stcg(reinterpret_cast<float4*>(P1 + o1), q1);
+    __stcg(gp1, z);
+    if (two) {
+      __stcg(reinterpret_cast<float4*>(W + o2), orx_apply4<OPT>(w2, g2, p2, q2, opt));
+      if (S0) __stcg(reinterpret_cast<float4*>(P0 + o2), p2);
+      if (S1) __stcg(reinterpret_cast<float4*>(P1 + o2), q2);
+      __stcg(gp2, z);
+    }
+  }
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(256) k_sh_tail(ShardDev x, ShardWs w, ShTailArgs u, ShApplyArgs a, int32_t* counters,
+                                                 float* out4) {
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   const int D = x.D;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  orx_pdl_wait();
   const int nu = counters[0], ni = counters[1];
-  for (int r = gwarp; r < ni; r += nw) {
-    const int id = a.hi.did[r];
-    for (int e = lane * 4; e < D; e += 128) {
-      const int64_t off = (int64_t)id * D + e;
-      float4* gp = reinterpret_cast<float4*>(a.gi + (int64_t)r * D + e);
-      const float4 g = __ldcg(gp);
-      float4 wv = __ldcg(reinterpret_cast<const float4*>(a.I + off));
-      float4 s0v = S0 ? __ldcg(reinterpret_cast<const float4*>(a.Is0 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 s1v = S1 ? __ldcg(reinterpret_cast<const float4*>(a.Is1 + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      __stcg(reinterpret_cast<float4*>(a.I + off), orx_apply4<OPT>(wv, g, s0v, s1v, a.opt));
-      if (S0) __stcg(reinterpret_cast<float4*>(a.Is0 + off), s0v);
-      if (S1) __stcg(reinterpret_cast<float4*>(a.Is1 + off), s1v);
-      __stcg(gp, make_float4(0.f, 0.f, 0.f, 0.f));
-    }
-    if (lane == 0) {
+  for (int r = gwarp; r < nu; r += 2 * nw) {
+    const int r2 = r + nw;
+    const bool two = r2 < nu;
+    sh_apply_staged2<OPT>(u.U, u.Us0, u.Us1, u.gu, D, lane, u.hu.did[r], r, two, two ? u.hu.did[r2] : 0, two ? r2 : r, a.opt);
+  }
+  for (int r = gwarp; r < ni; r += 2 * nw) {
+    const int r2 = r + nw;
+    const bool two = r2 < ni;
+    const int id1 = a.hi.did[r], id2 = two ? a.hi.did[r2] : 0;
+    sh_apply_staged2<OPT>(a.I, a.Is0, a.Is1, a.gi, D, lane, id1, r, two, id2, two ? r2 : r, a.opt);
+    if (lane < (two ? 2 : 1)) {            // lane 0: row r, lane 1: row r2 -- the item bias of the staged row
+      const int id = lane ? id2 : id1, rr = lane ? r2 : r;
       float s0v = S0 ? a.Bs0[id] : 0.f, s1v = S1 ? a.Bs1[id] : 0.f;
-      a.Bv[id] = orx_apply<OPT>(a.Bv[id], __ldcg(a.gb + r), s0v, s1v, a.opt);
+      a.Bv[id] = orx_apply<OPT>(a.Bv[id], __ldcg(a.gb + rr), s0v, s1v, a.opt);
       if (S0) a.Bs0[id] = s0v;
       if (S1) a.Bs1[id] = s1v;
-      a.gb[r] = 0.f;
+      a.gb[rr] = 0.f;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {    // every rank adds the R pairs it holds in rank order: bit-identical totals
@@ -715,7 +757,6 @@ __global__ void __launch_bounds__(256) k_sh_item_tail(ShardDev x, ShardWs w, ShA
 struct orx_shard_ws {
   ShardWs w;
   int home_cap, gin_cap, got_rows;
-  int n_partials;   // warps of the last k_sh_compute grid (k_sh_finish reduces that many pairs)
 };
 
 // ---- IPC-exportable device memory: every rank maps every other rank's mailboxes (cudaIpc*, one box, NVLink) ----
@@ -776,7 +817,6 @@ static void shard_ws_free(orx_ctx* c) {
   cudaFree(s->w.trip_u);
   cudaFree(s->w.slot);
   cudaFree(s->w.req);
-  cudaFree(s->w.gbs);
   cudaFree(s->w.ctl);
   delete s;
   c->shard_ws = nullptr;
@@ -796,10 +836,8 @@ static int shard_ws_ensure(orx_ctx* c, const ShardHost* x, cudaStream_t st) {
   ORX_CUDA(cudaMalloc(&s->w.trip_u, sizeof(int32_t) * (size_t)x->home_cap));
   ORX_CUDA(cudaMalloc(&s->w.slot, sizeof(int32_t) * 2 * (size_t)x->home_cap));
   ORX_CUDA(cudaMalloc(&s->w.req, sizeof(int32_t) * (size_t)x->gin_cap));
-  ORX_CUDA(cudaMalloc(&s->w.gbs, sizeof(float) * (size_t)got_rows));
   ORX_CUDA(cudaMalloc(&s->w.ctl, sizeof(int32_t) * SH_C_WORDS));
   ORX_CUDA(cudaMemsetAsync(s->w.ctl, 0, sizeof(int32_t) * SH_C_WORDS, st));
-  ORX_CUDA(cudaMemsetAsync(s->w.gbs, 0, sizeof(float) * (size_t)got_rows, st));
   s->home_cap = x->home_cap;
   s->gin_cap = x->gin_cap;
   s->got_rows = got_rows;
@@ -850,7 +888,7 @@ static int launch_compute(int nq, int num_sms, cudaStream_t st, const ShardDev& 
 #define SH_GO(NQ)                                                                        \
   {                                                                                      \
     const int g = num_sms * sh_ctas_per_sm((const void*)k_sh_compute<KIND, OPT, NQ>, 4); \
-    k_sh_compute<KIND, OPT, NQ><<<g, 256, 0, st>>>(xd, w, a, epoch);                     \
+    orx_launch_pdl(k_sh_compute<KIND, OPT, NQ>, dim3(g), dim3(256), 0, st, xd, w, a, epoch); \
     return g;                                                                            \
   }
   if (nq <= 32) SH_GO(1) else if (nq <= 64) SH_GO(2) else SH_GO(4)
@@ -861,14 +899,13 @@ static void launch_apply(int nq, int num_sms, cudaStream_t st, const ShardDev& x
 #define SH_GO(NQ)                                                                   \
   {                                                                                 \
     const int g = num_sms * sh_ctas_per_sm((const void*)k_sh_apply<OPT, NQ>, 4);    \
-    k_sh_apply<OPT, NQ><<<g, 256, 0, st>>>(xd, w, a, epoch);                        \
+    orx_launch_pdl(k_sh_apply<OPT, NQ>, dim3(g), dim3(256), 0, st, xd, w, a, epoch); \
   }
   if (nq <= 32) SH_GO(1) else if (nq <= 64) SH_GO(2) else SH_GO(4)
 #undef SH_GO
 }
 
-// One step (or a sub-range of its seven launches: phases 0 route, 1 request, 2 serve, 3 compute, 4 finish, 5 apply,
-// 6 item tail).  See the file header.  out4 = { loss, l2_loss, skipped triplets (ids out of range), staged rows }, the
+// One step (or a sub-range of its six launches: phases 0 route, 1 request, 2 serve, 3 compute, 4 apply, 5 tail).  See the file header.  out4 = { loss, l2_loss, skipped triplets (ids out of range), staged rows }, the
 // first two GLOBAL and identical on every rank.
 extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* xs, const orx_table_t* user,
                               const orx_table_t* item, const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid,
@@ -883,7 +920,7 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
   ORX_REQUIRE(user->dim == x->dim && item->dim == x->dim && item_bias->dim == 1 && item_bias->rows == item->rows, "table shapes");
   ORX_REQUIRE(B > 0 && B <= x->batch_cap && uid && pid && nid, "bad batch (larger than the mailboxes were built for?)");
   ORX_REQUIRE(total_users > 0 && total_items > 0 && epoch > 0, "bad totals / epoch");
-  ORX_REQUIRE(phase_lo >= 0 && phase_hi <= 6 && phase_lo <= phase_hi, "bad phase range");
+  ORX_REQUIRE(phase_lo >= 0 && phase_hi <= 5 && phase_lo <= phase_hi, "bad phase range");
   ORX_REQUIRE(opt->kind == ORX_OPT_SGD || opt->kind == ORX_OPT_ADAGRAD || opt->kind == ORX_OPT_ADAM_LAZY,
               "the sharded step supports SGD, Adagrad and row-sparse Adam");
   if (opt->kind != ORX_OPT_SGD) ORX_REQUIRE(user->s0 && item->s0 && item_bias->s0, "optimizer slot s0 missing");
@@ -900,33 +937,39 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
     if ((rc = orx_next_epoch(h, st))) return rc;
   const OrxOptDev od = orx_opt_to_dev(opt);
   const int nq = x->dim >> 2;
-  orx_shard_ws* wsp = (orx_shard_ws*)h->shard_ws;
   if ((rc = orx_ensure_partials(h, h->num_sms * 4 * 8, st))) return rc;   // compute grid <= 4 CTAs/SM x 8 warps
   ShCompArgs ca;
   ca.U = user->var; ca.Us0 = user->s0; ca.Us1 = user->s1; ca.hu = h->hu; ca.gu = h->gu;
   ca.margin = margin; ca.c_loss = c_loss; ca.c_l2 = c_l2; ca.inv_B = inv_B; ca.opt = od; ca.partials = h->partials;
+  ca.loss_scale = kind == ORX_PAIR_BPR ? inv_B : 1.f;
   ShApplyArgs aa;
   aa.I = item->var; aa.Is0 = item->s0; aa.Is1 = item->s1;
   aa.Bv = item_bias->var; aa.Bs0 = item_bias->s0; aa.Bs1 = item_bias->s1;
   aa.hi = h->hi; aa.gi = h->gi; aa.gb = h->gb; aa.opt = od;
+  const bool whole = phase_lo == 0 && phase_hi == 5;     // the measurement hook follows whole steps only
   for (int ph = phase_lo; ph <= phase_hi; ++ph) {
+    if (whole) orx_prof_mark(h, ph, st);
     switch (ph) {
       case 0:
-        k_sh_route<<<(B + 1023) / 1024, 256, 0, st>>>(xd, w, uid, pid, nid, B, total_users, total_items, epoch);
+        ORX_CUDA(orx_launch_pdl(k_sh_route, dim3((B + 1023) / 1024), dim3(256), 0, st, xd, w, uid, pid, nid, B, total_users,
+                                total_items, epoch));
         break;
       case 1: {
         int g = (x->home_cap + 511) / 512;
         if (g > h->num_sms * 4) g = h->num_sms * 4;
-        k_sh_request<<<g, 256, 0, st>>>(xd, w, h->hu, epoch);
+        ORX_CUDA(orx_launch_pdl(k_sh_request, dim3(g), dim3(256), 0, st, xd, w, h->hu, epoch));
         break;
       }
       case 2:
-        if (nq <= 32) k_sh_serve<1><<<h->num_sms * 4, 256, 0, st>>>(xd, w, item->var, item_bias->var, item->rows, h->hi, epoch);
-        else if (nq <= 64) k_sh_serve<2><<<h->num_sms * 4, 256, 0, st>>>(xd, w, item->var, item_bias->var, item->rows, h->hi, epoch);
-        else k_sh_serve<4><<<h->num_sms * 2, 256, 0, st>>>(xd, w, item->var, item_bias->var, item->rows, h->hi, epoch);
+#define SH_SERVE(NQ)                                                                                          \
+  ORX_CUDA(orx_launch_pdl(k_sh_serve<NQ>, dim3(h->num_sms * sh_ctas_per_sm((const void*)k_sh_serve<NQ>, 4)),  \
+                          dim3(256), 0, st, xd, w, (const float*)item->var, (const float*)item_bias->var,    \
+                          (int64_t)item->rows, h->hi, epoch))
+        if (nq <= 32) SH_SERVE(1); else if (nq <= 64) SH_SERVE(2); else SH_SERVE(4);
+#undef SH_SERVE
         break;
       case 3:
-#define SH_COMPUTE(K, O) wsp->n_partials = 8 * launch_compute<K, O>(nq, h->num_sms, st, xd, w, ca, epoch)
+#define SH_COMPUTE(K, O) launch_compute<K, O>(nq, h->num_sms, st, xd, w, ca, epoch)
         if (kind == ORX_PAIR_BPR) {
           if (opt->kind == ORX_OPT_SGD) SH_COMPUTE(ORX_PAIR_BPR, ORX_OPT_SGD);
           else if (opt->kind == ORX_OPT_ADAGRAD) SH_COMPUTE(ORX_PAIR_BPR, ORX_OPT_ADAGRAD);
@@ -938,28 +981,26 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
         }
 #undef SH_COMPUTE
         break;
-      case 4: {
-        const float ls = kind == ORX_PAIR_BPR ? inv_B : 1.f;
-        const int g = h->num_sms * 2, np = wsp->n_partials;
-        if (opt->kind == ORX_OPT_SGD) k_sh_finish<ORX_OPT_SGD><<<g, 256, 0, st>>>(xd, w, ca, np, ls, h->counters, epoch);
-        else if (opt->kind == ORX_OPT_ADAGRAD) k_sh_finish<ORX_OPT_ADAGRAD><<<g, 256, 0, st>>>(xd, w, ca, np, ls, h->counters, epoch);
-        else k_sh_finish<ORX_OPT_ADAM_LAZY><<<g, 256, 0, st>>>(xd, w, ca, np, ls, h->counters, epoch);
-        break;
-      }
-      case 5:
+      case 4:
         if (opt->kind == ORX_OPT_SGD) launch_apply<ORX_OPT_SGD>(nq, h->num_sms, st, xd, w, aa, epoch);
         else if (opt->kind == ORX_OPT_ADAGRAD) launch_apply<ORX_OPT_ADAGRAD>(nq, h->num_sms, st, xd, w, aa, epoch);
         else launch_apply<ORX_OPT_ADAM_LAZY>(nq, h->num_sms, st, xd, w, aa, epoch);
         break;
-      case 6: {
-        const int g = h->num_sms * 2;
-        if (opt->kind == ORX_OPT_SGD) k_sh_item_tail<ORX_OPT_SGD><<<g, 256, 0, st>>>(xd, w, aa, h->counters, out4);
-        else if (opt->kind == ORX_OPT_ADAGRAD) k_sh_item_tail<ORX_OPT_ADAGRAD><<<g, 256, 0, st>>>(xd, w, aa, h->counters, out4);
-        else k_sh_item_tail<ORX_OPT_ADAM_LAZY><<<g, 256, 0, st>>>(xd, w, aa, h->counters, out4);
+      case 5: {
+        const int g = h->num_sms * 4;
+        ShTailArgs ta;
+        ta.U = user->var; ta.Us0 = user->s0; ta.Us1 = user->s1; ta.hu = h->hu; ta.gu = h->gu;
+        if (opt->kind == ORX_OPT_SGD) ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_SGD>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, h->counters, out4));
+        else if (opt->kind == ORX_OPT_ADAGRAD) ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_ADAGRAD>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, h->counters, out4));
+        else ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_ADAM_LAZY>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, h->counters, out4));
         break;
       }
     }
     ORX_LAUNCH_CHECK();
+  }
+  if (whole) {
+    orx_prof_mark(h, 6, st);
+    orx_prof_next(h);
   }
   return ORX_OK;
 }

@@ -77,12 +77,12 @@ class Engine:
     def profile_enable(self, on=True):
         _lib.check(self.lib.orx_profile_enable(self.h, 1 if on else 0))
 
-    def profile_read(self):
-        """-> ([ms_index, ms_step, ms_tail] summed over the recorded steps, n_steps)."""
-        ms = (C.c_float * 3)()
+    def profile_read(self, n_phases=3):
+        """-> ([ms per phase] summed over the recorded steps, n_steps); phases: see orx_profile_enable in orx.h."""
+        ms = (C.c_float * n_phases)()
         n = C.c_int32()
-        _lib.check(self.lib.orx_profile_read(self.h, ms, C.byref(n)))
-        return [ms[0], ms[1], ms[2]], n.value
+        _lib.check(self.lib.orx_profile_read(self.h, ms, n_phases, C.byref(n)))
+        return list(ms), n.value
 
     # ---- LatentFactor ------------------------------------------------------------------
     def fill_uniform(self, dst, lo, hi, seed):

@@ -156,7 +156,7 @@ class HomeRoutedPairwise:
     """Row-sharded BPR (kind 0) / UCML (kind 1) step, "home-routed" (csrc/orx_shard.cu): row r of the user and item
     tables lives on rank ``r % R``; a triplet is computed on the rank that owns its USER row, so only the two item rows
     travel in and the two item gradient rows travel out, as peer stores of aligned rows into IPC-mapped mailboxes.  One
-    C call per step (seven launches, flag words in peer memory instead of barriers, no collective, no host sync).
+    C call per step (six launches, flag words in peer memory instead of barriers, no collective, no host sync).
     ``torch.distributed`` is used once, to swap the 64-byte IPC handles.
 
     ``peers=None``: the R ranks are R processes (one per GPU) and the mailboxes are exchanged over ``torch.distributed``.
@@ -224,7 +224,7 @@ class HomeRoutedPairwise:
         self._out = torch.zeros(16, 4, dtype=torch.float32, device=dev)     # ring of step outputs
         self._tabs = (eng.make_table(self.user, *self.user_slots), eng.make_table(self.item, *self.item_slots),
                       eng.make_table(self.bias, *self.bias_slots))
-        self.launches_per_step = 7
+        self.launches_per_step = 6
 
     def _set_pointers(self, ptrs):
         self._ptrs = torch.from_numpy(np.ascontiguousarray(ptrs)).to(self.eng.device)
@@ -255,7 +255,7 @@ class HomeRoutedPairwise:
         if self._loop is not None:
             raise RuntimeError("loopback ranks are stepped by their LoopbackGroup")
         self.iterations += 1
-        return self._call(uid, pid, nid, c_loss, c_l2, 0, 6)[:2]
+        return self._call(uid, pid, nid, c_loss, c_l2, 0, 5)[:2]
 
     def check(self):
         """Raise if a flag wait timed out or a mailbox overflowed (sticky device word; one tiny D2H read)."""
@@ -331,7 +331,7 @@ class HomeRoutedPairwise:
 
 class LoopbackGroup:
     """R virtual ranks of HomeRoutedPairwise on ONE device and ONE stream: every rank has its own liborx handle, tables
-    and mailboxes (plain device memory); a step issues phase k of the seven launches for every rank before phase k + 1,
+    and mailboxes (plain device memory); a step issues phase k of the six launches for every rank before phase k + 1,
     so every flag a kernel waits for is already set.  Same kernels, same peer-pointer tables as the multi-GPU step."""
 
     def __init__(self, world, total_users, total_items, dim, batch, device=None, **kw):
@@ -358,7 +358,7 @@ class LoopbackGroup:
         for m in self.ranks:
             m.iterations += 1
         outs = [None] * self.world
-        for ph in range(7):
+        for ph in range(6):
             for r, m in enumerate(self.ranks):
                 outs[r] = m._call(*batches[r], c_loss, c_l2, ph, ph)
         return [o[:2] for o in outs]
@@ -391,7 +391,7 @@ class LoopbackGroup:
 # ---------------------------------------------------------------------------------------
 # bench.py's N>1 leg
 # ---------------------------------------------------------------------------------------
-def bench(args, rank, world, eng, barrier):
+def bench(args, rank, world, eng, barrier, clocks=None):
     import bench as B
     from . import native as N
     K, W = args.steps, max(3, args.warmup)
@@ -407,63 +407,50 @@ def bench(args, rank, world, eng, barrier):
     host_ids = [tuple(torch.randint(0, n, (Bsz,), generator=g, dtype=torch.int32).pin_memory() for n in (U, I, I))
                 for _ in range(B.N_BATCHES)]
     dev_ids = [tuple(x.to(dev) for x in b) for b in host_ids]
-    clocks = B.ClockSampler(dev.index or 0) if rank == 0 else None
-    for i in range(W):
+
+    def step(i):
         model.step(*dev_ids[i % B.N_BATCHES], reduce_loss=False)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    e0.record()
-    for i in range(K):
-        model.step(*dev_ids[i % B.N_BATCHES], reduce_loss=False)   # loss stays a per-rank partial on the device
-    e1.record()
-    barrier()
-    t1 = time.time()
-    seconds = e0.elapsed_time(e1) * 1e-3
-    if clocks:
-        clocks.window(t0, t1)
-    # e2e: pinned host ids in, global loss out to the host, every step
-    last = 0.0
+
     for i in range(W):
-        last = model.step(*(x.to(dev, non_blocking=True) for x in host_ids[i % B.N_BATCHES])).cpu()
-    barrier()
-    t0 = time.time()
-    e0.record()
+        step(i)
+    seconds = B._timed(step, K, barrier, torch, clocks)
+    # e2e: pinned host ids in, global loss out to the host, every step (read one step behind, so the copy overlaps)
     pinned = [torch.zeros(2).pin_memory() for _ in range(2)]
-    prev = None
-    for i in range(K):
-        out = model.step(*(x.to(dev, non_blocking=True) for x in host_ids[i % B.N_BATCHES]))   # global loss
+    state = {"prev": None, "last": None}
+
+    def e2e_step(i):
+        out = model.step(*(x.to(dev, non_blocking=True) for x in host_ids[i % B.N_BATCHES]))   # global (loss, l2)
         pinned[i & 1].copy_(out, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        if prev is not None:                      # read every step's loss on the host, one step behind
-            prev[0].synchronize()
-            last = prev[1].clone()
-        prev = (ev, pinned[i & 1])
-    prev[0].synchronize()
-    last = prev[1].clone()
-    e1.record()
-    barrier()
-    t1 = time.time()
-    if clocks:
-        clocks.window(t0, t1)
-    e2e_seconds = e0.elapsed_time(e1) * 1e-3
+        if state["prev"] is not None:
+            state["prev"][0].synchronize()
+            state["last"] = state["prev"][1].clone()
+        state["prev"] = (ev, pinned[i & 1])
+
+    for i in range(W):
+        e2e_step(i)
+    e2e_seconds = B._timed(e2e_step, K, barrier, torch, clocks)
+    state["prev"][0].synchronize()
+    last = state["prev"][1].clone()
     if hasattr(model, "check"):
         model.check()
-    # NVLink-bound exchange: bytes per GPU per direction per step
-    link_bytes = 2.0 * (world - 1) / world * ((2 if mode == "home" else 3) * (D + 1)) * 4 * Bsz
+    # NVLink-bound exchange: bytes per GPU per direction per step: rows out as owner + gradient rows out as home
+    rows_each_way = 2 if mode == "home" else 3
+    link_bytes = 2.0 * (world - 1) / world * rows_each_way * (D + 1) * 4 * Bsz
     nvlink_peak = 770.0
-    roofline = {"bound": "nvlink", "achieved": link_bytes / (seconds / K) / 1e9, "peak": nvlink_peak, "unit": "GB/s",
+    ms = seconds / K * 1e3
+    roofline = {"bound": "nvlink", "kernel": "k_sh_serve + k_sh_compute (peer stores)" if mode == "home" else "NCCL all-to-all",
+                "achieved": link_bytes / (seconds / K) / 1e9, "peak": nvlink_peak, "unit": "GB/s",
                 "frac": link_bytes / (seconds / K) / 1e9 / nvlink_peak, "traffic": None,
                 "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s per direction per GPU",
                 "algorithmic_bytes_per_launch": link_bytes,
-                "note": "per-GPU per-direction NVLink bytes of the row + gradient exchange; the N=1 line carries "
-                        "the HBM roofline of the fused kernel"}
-    return {"seconds": seconds, "e2e_seconds": e2e_seconds,
-            "clocks": clocks.stop() if clocks else None, "launches": model.launches_per_step * K * world,
-            "roofline": roofline,
-            "e2e_api": f"openrec_b200.{type(model).__module__.split('.')[-1]}.{type(model).__name__}.step"
-                       "; pinned host ids in, global loss to host each step",
+                "note": f"per-GPU per-direction NVLink bytes of the item-row + gradient-row exchange ({rows_each_way} rows each way "
+                        f"per triplet, (N-1)/N of them remote) over the WHOLE step time ({ms:.3f} ms): the step also does the local "
+                        "HBM work of the single-GPU step; the N = 1 line carries the HBM roofline of the fused kernel"}
+    return {"seconds": seconds, "e2e_seconds": e2e_seconds, "launches": model.launches_per_step * K * world,
+            "units_per_step": Bsz, "h2d": 3 * 4 * Bsz, "d2h": 8, "roofline": roofline,
+            "e2e_api": f"openrec_b200.sharded.{type(model).__name__}.step; pinned host ids in, global loss to host each step",
             "extra": {"last_loss": [float(x) for x in last], "total_items": I, "total_users": U,
                       "exchange": {"home": "home-routed: triplets computed on the user row's owner; item rows / gradient rows "
                                            "as peer stores into IPC-mapped mailboxes over NVLink, flag words instead of "

@@ -3,21 +3,58 @@ DLRM forward/backward composition -- all arithmetic in liborx (orx_mlp_layer_*, 
 orx_gather_strided, orx_pred_loss); this module only sequences launches and owns activations."""
 from __future__ import annotations
 
-import os
-
 import torch
 
 from .. import native as N
 
-# ORX_DLRM_PAD=1 (experimental): give (dense_vec | interactions) and its gradient a leading dimension that is a multiple
-# of 4 floats, so that every row of the 479-wide top-MLP input is 16-byte aligned (128-bit loads / cp.async in the
-# Dense-layer kernels).  The kernels take explicit leading dimensions, nothing else changes.
-_PAD = os.environ.get("ORX_DLRM_PAD", "0") == "1"
+GEMM_KERNEL_NAME = "k_gemm_tc2 (tcgen05 kind::tf32, 3xTF32, 128x128 tile, TMEM accumulators)"
 
 
 def _rows(B, n, device):
-    ld = (n + 3) // 4 * 4 if _PAD else n
-    return torch.empty(B, ld, dtype=torch.float32, device=device)[:, :n]
+    return torch.empty(B, n, dtype=torch.float32, device=device)
+
+
+class GemmProfile:
+    """bench.py's roofline hook: while active, every Dense-layer GEMM call (forward, and the dgrad + wgrad pair of a
+    backward call) is bracketed by CUDA events on the launch stream; totals() -> (ms, flops, calls)."""
+    active = None
+
+    def __enter__(self):
+        self.ev = []
+        GemmProfile.active = self
+        return self
+
+    def __exit__(self, *a):
+        GemmProfile.active = None
+
+    def bracket(self, flops):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.ev.append((e0, e1, flops))
+        return e0, e1
+
+    def totals(self):
+        torch.cuda.synchronize()
+        return (sum(a.elapsed_time(b) for a, b, _ in self.ev), float(sum(f for _, _, f in self.ev)), len(self.ev))
+
+
+def _mlp_fwd(eng, x, w, b, act, y):
+    p = GemmProfile.active
+    if p is None:
+        return eng.mlp_fwd(x, w, b, act, y)
+    e0, e1 = p.bracket(2.0 * x.shape[0] * w.shape[0] * w.shape[1])
+    e0.record()
+    eng.mlp_fwd(x, w, b, act, y)
+    e1.record()
+
+
+def _mlp_bwd(eng, x, y, w, act, dy, dx, dw, db):
+    p = GemmProfile.active
+    if p is None:
+        return eng.mlp_bwd(x, y, w, act, dy, dx, dw, db)
+    e0, e1 = p.bracket((4.0 if dx is not None else 2.0) * x.shape[0] * w.shape[0] * w.shape[1])
+    e0.record()
+    eng.mlp_bwd(x, y, w, act, dy, dx, dw, db)
+    e1.record()
 
 ACT = {None: 0, "linear": 0, "relu": 1, "sigmoid": 2}
 
@@ -69,7 +106,7 @@ class DLRMGraph:
             if last and w.shape[1] != D:
                 raise ValueError("the bottom MLP's last width must equal m_spa (tf.stack in the interaction)")
             y = top_in[:, :D] if last else torch.empty(B, w.shape[1], dtype=torch.float32, device=dev)
-            eng.mlp_fwd(x, w, b, act, y)
+            _mlp_fwd(eng, x, w, b, act, y)
             acts.append(y)
             x = y
         c["bot_acts"] = acts
@@ -77,7 +114,7 @@ class DLRMGraph:
         x, acts = top_in, []
         for w, b, act in self.top:
             y = torch.empty(B, w.shape[1], dtype=torch.float32, device=dev)
-            eng.mlp_fwd(x, w, b, act, y)
+            _mlp_fwd(eng, x, w, b, act, y)
             acts.append(y)
             x = y
         c["top_acts"] = acts
@@ -104,7 +141,7 @@ class DLRMGraph:
             dx = d_top_in if l == 0 else torch.empty(B, w.shape[0], dtype=torch.float32, device=dev)
             dw = torch.empty_like(w)
             db = torch.empty_like(b) if b is not None else None
-            eng.mlp_bwd(x, c["top_acts"][l], w, act, dy, dx, dw, db)
+            _mlp_bwd(eng, x, c["top_acts"][l], w, act, dy, dx, dw, db)
             top_g[l] = (dw, db)
             dy = dx
         dZ = torch.empty_like(Z)
@@ -117,7 +154,7 @@ class DLRMGraph:
             dx = None if l == 0 else torch.empty(B, w.shape[0], dtype=torch.float32, device=dev)
             dw = torch.empty_like(w)
             db = torch.empty_like(b) if b is not None else None
-            eng.mlp_bwd(x, c["bot_acts"][l], w, act, dy, dx, dw, db)
+            _mlp_bwd(eng, x, c["bot_acts"][l], w, act, dy, dx, dw, db)
             bot_g[l] = (dw, db)
             dy = dx
         return dZ, bot_g, top_g

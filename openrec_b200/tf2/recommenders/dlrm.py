@@ -109,6 +109,14 @@ class DLRM(Model):
         node.stepped = True
         node.inputs = None
 
+    def _launches_per_step(self):
+        """liborx kernel launches of one training step (bench.py's gpu_launches): per table gather + index / apply / tail,
+        per Dense layer forward (1) + backward (activation, column sum, dgrad, wgrad; split-K adds a reduce) + 2 dense
+        applies, 2 interaction kernels, 1 loss kernel."""
+        T = len(self._latent_factors)
+        n_dense = len(self._mlp_bot.layers) + len(self._mlp_top.layers)
+        return 4 * T + n_dense * (1 + 4 + 2) + 2 + 1
+
     def _orx_materialize_grad(self, node, var, coef):
         if node.stepped:
             raise RuntimeError("gradients requested after the step was applied")
