@@ -7,11 +7,15 @@ import torch
 
 from .. import native as N
 
-GEMM_KERNEL_NAME = "k_gemm_tc2 (tcgen05 kind::tf32, 3xTF32, 128x128 tile, TMEM accumulators)"
+GEMM_KERNEL_NAME = "k_gemm_tma (TMA-fed tcgen05 kind::tf32, 3xTF32, 128x256 tile, TMEM accumulators)"
 
 
 def _rows(B, n, device):
-    return torch.empty(B, n, dtype=torch.float32, device=device)
+    """[B, n] activations whose row stride is a multiple of 4 floats: the TMA descriptors of the Dense-layer GEMMs need
+    16-byte row strides (the 479-wide (dense_vec | interactions) block gets ld = 480); kernels take explicit strides."""
+    ld = (n + 3) // 4 * 4
+    t = torch.empty(B, ld, dtype=torch.float32, device=device)
+    return t if ld == n else t[:, :n]
 
 
 class GemmProfile:

@@ -8,8 +8,9 @@ eng = N.engine()
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 B = 32768
 for (K, Nn) in [(1024, 1024), (479, 1024), (1024, 512), (512, 256), (256, 128), (512, 256)]:
-    x = torch.randn(B, K, device='cuda'); w = torch.randn(K, Nn, device='cuda') * 0.03; b = torch.zeros(Nn, device='cuda')
-    y = torch.empty(B, Nn, device='cuda'); dy = torch.randn(B, Nn, device='cuda'); dx = torch.empty(B, K, device='cuda')
+    Kp = (K + 3) // 4 * 4                      # row stride a multiple of 16 bytes, as DLRMGraph allocates (TMA)
+    x = torch.randn(B, Kp, device='cuda')[:, :K]; w = torch.randn(K, Nn, device='cuda') * 0.03; b = torch.zeros(Nn, device='cuda')
+    y = torch.empty(B, Nn, device='cuda'); dy = torch.randn(B, Nn, device='cuda'); dx = torch.empty(B, Kp, device='cuda')[:, :K]
     dw = torch.empty_like(w); db = torch.empty_like(b)
     def t(fn):
         for _ in range(3): fn()

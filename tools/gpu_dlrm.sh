@@ -1,7 +1,8 @@
 #!/bin/bash
-TAG=$1
+# One GPU: DLRM parity tests, Dense-layer GEMM accuracy + speed probes, DLRM bench line.   usage: tools/gpu_dlrm.sh TAG
+TAG=${1:-dlrm}
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_dlrm.py -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1; tail -3 gpurun_out/${TAG}_pytest.log; grep -n "^FAILED\|^ERROR" gpurun_out/${TAG}_pytest.log | head
-PYTHONPATH=compat:. python tools/bench_dlrm.py --steps 10 2>&1 | tail -1 | tee gpurun_out/${TAG}_dlrm.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 450 -c 600 --csv --log-file gpurun_out/${TAG}_dlrm_launches.csv env PYTHONPATH=compat:. python tools/bench_dlrm.py --steps 3 --vocab 100000 > gpurun_out/${TAG}_ncu.log 2>&1
-wc -l gpurun_out/${TAG}_dlrm_launches.csv
+timeout 600 python -m pytest tests/test_gpu_dlrm.py -q -m gpu -x 2>&1 | tail -12
+timeout 300 python tools/tc_probe.py 2>&1 | tail -14
+timeout 300 python tools/gemm_probe.py 10 2>&1 | tail -7
+timeout 600 python bench.py --workload dlrm --steps 10 --warmup 3 --no-cpu > gpurun_out/${TAG}_bench_dlrm.json 2> gpurun_out/${TAG}_bench_dlrm.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/${TAG}_bench_dlrm.json; tail -3 gpurun_out/${TAG}_bench_dlrm.err
