@@ -2,7 +2,7 @@
 //
 // DLRM's MLPs (openrec/tf2/modules/multi_layer_perceptron.py:5-18, recommenders/dlrm.py:34-37,87,90-95) are the one
 // dense contraction on the path.  The parity bar is 1e-5 against an fp32 reference, which plain TF32 (10-bit mantissa)
-// cannot meet, so every fp32 operand is split into two TF32 terms (hi = TF32(v), lo = TF32(v - hi), round to nearest)
+// cannot meet, so every fp32 operand is split into two TF32 terms (hi = TF32(v) rounded to nearest, lo = v - hi)
 // and  C += Ahi*Bhi + Ahi*Blo + Alo*Bhi  is accumulated in fp32 (3xTF32, relative error ~2^-21 per product).
 //
 // One CTA computes a 128 x TN tile (TN = 256, or 128 for narrow outputs) of  C[M,N] = op(A)[M,K] * op(B)[K,N], K in
@@ -88,18 +88,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
-// hi = TF32(v) and lo = TF32(v - hi), both rounded to nearest (cvt.rna): truncation would bias every product
-// the same way and the error would grow linearly with K instead of with sqrt(K).
+// hi = TF32(v) rounded to nearest (cvt.rna: truncation would bias every product the same way and the error would grow
+// linearly with K instead of with sqrt(K)); lo = v - hi exactly (|lo| <= 2^-11 |v|).  lo is handed to the tensor core as
+// it is: kind::tf32 reads the top 19 bits, i.e. truncates lo by at most 2^-10 |lo| <= 2^-21 |v| -- the size of the
+// lo*lo term 3xTF32 drops anyway, and of random sign because hi was rounded to nearest.
 __device__ __forceinline__ float to_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return __uint_as_float(r);
 }
 __device__ __forceinline__ void split4(const float4 v, float4* hi, float4* lo) {
-  hi->x = to_tf32(v.x); lo->x = to_tf32(v.x - hi->x);
-  hi->y = to_tf32(v.y); lo->y = to_tf32(v.y - hi->y);
-  hi->z = to_tf32(v.z); lo->z = to_tf32(v.z - hi->z);
-  hi->w = to_tf32(v.w); lo->w = to_tf32(v.w - hi->w);
+  hi->x = to_tf32(v.x); lo->x = v.x - hi->x;
+  hi->y = to_tf32(v.y); lo->y = v.y - hi->y;
+  hi->z = to_tf32(v.z); lo->z = v.z - hi->z;
+  hi->w = to_tf32(v.w); lo->w = v.w - hi->w;
 }
 
 // One warp-item of the conversion: 32 (row, 4-k group) pairs of a raw tile -> hi / lo operand tiles.
@@ -108,19 +110,29 @@ __device__ __forceinline__ void split4(const float4 v, float4* hi, float4* lo) {
 //              eight rows of one k-core (8 distinct bank groups thanks to the swizzle) and writes 128 contiguous bytes.
 //  KC = false: raw is [16 k][R rows]; item `wi` covers k-core wi & 3 of rows 32*(wi >> 2) .. +31: four coalesced scalar
 //              loads per lane, one 128-bit store per tile (a quarter-warp again writes 128 contiguous bytes).
+// The byte offsets of an item inside a raw stage / an operand tile do not depend on the k-block: computed once per thread.
 template <bool KC>
-__device__ __forceinline__ void convert_item(const unsigned char* raw, int R, int wi, int lane, unsigned char* hi_tile,
-                                             unsigned char* lo_tile) {
-  float4 v;
+__device__ __forceinline__ void item_offsets(int R, int wi, int lane, int* src_off, int* dst_off) {
   int row, kcore;
   if (KC) {
     row = 8 * wi + (lane & 7);
     kcore = lane >> 3;
-    v = *reinterpret_cast<const float4*>(raw + row * 64 + ((kcore ^ ((row >> 1) & 3)) << 4));
+    *src_off = row * 64 + ((kcore ^ ((row >> 1) & 3)) << 4);
   } else {
     row = 32 * (wi >> 2) + lane;
     kcore = wi & 3;
-    const float* p = reinterpret_cast<const float*>(raw) + (size_t)(kcore * 4) * R + row;
+    *src_off = (kcore * 4 * R + row) * 4;
+  }
+  *dst_off = (row >> 3) * OP_SBO + kcore * 128 + (row & 7) * 16;
+}
+template <bool KC, int R>
+__device__ __forceinline__ void convert_item(const unsigned char* raw, int src_off, int dst_off, unsigned char* hi_tile,
+                                             unsigned char* lo_tile) {
+  float4 v;
+  if (KC) {
+    v = *reinterpret_cast<const float4*>(raw + src_off);
+  } else {
+    const float* p = reinterpret_cast<const float*>(raw + src_off);
     v.x = p[0];
     v.y = p[R];
     v.z = p[2 * R];
@@ -128,9 +140,8 @@ __device__ __forceinline__ void convert_item(const unsigned char* raw, int R, in
   }
   float4 h, l;
   split4(v, &h, &l);
-  const int off = (row >> 3) * OP_SBO + kcore * 128 + (row & 7) * 16;
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
+  *reinterpret_cast<float4*>(hi_tile + dst_off) = h;
+  *reinterpret_cast<float4*>(lo_tile + dst_off) = l;
 }
 
 template <int TN>
@@ -206,21 +217,23 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
+      const uint64_t desc0 = make_desc(smem_u32(op_ring));
       for (int kb = 0; kb < nkb; ++kb) {
         const int os = kb % OP_STAGES, g = kb / GROUP_KB;
         const bool g_first = (kb % GROUP_KB) == 0, g_last = (kb % GROUP_KB) == GROUP_KB - 1 || kb == nkb - 1;
         if (g_first && g >= 2) mbar_wait(&acc_empty[g & 1], ((g >> 1) - 1) & 1);   // group g-2 has been drained from this buffer
         mbar_wait(&op_full[os], (kb / OP_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = smem_u32(op_ring + (size_t)os * G::OP_STAGE), a_lo = a_hi + G::OP_A, b_hi = a_lo + G::OP_A,
-                       b_lo = b_hi + G::OP_B;
+        // descriptors: the address field is the low 14 bits (16-byte units), everything else is constant
+        const uint64_t a_hi = desc0 + (uint64_t)(os * (G::OP_STAGE >> 4)), a_lo = a_hi + (G::OP_A >> 4),
+                       b_hi = a_lo + (G::OP_A >> 4), b_lo = b_hi + (G::OP_B >> 4);
         const uint32_t d = tmem_d + (uint32_t)((g & 1) * TN);
 #pragma unroll
         for (int ks = 0; ks < TK / 8; ++ks) {
-          const uint32_t o = ks * 256;                         // two k-cores of 128 bytes
-          mma_tf32<TN>(d, make_desc(a_hi + o), make_desc(b_hi + o), (g_first && ks == 0) ? 0u : 1u);
-          mma_tf32<TN>(d, make_desc(a_hi + o), make_desc(b_lo + o), 1u);
-          mma_tf32<TN>(d, make_desc(a_lo + o), make_desc(b_hi + o), 1u);
+          const uint64_t o = (uint64_t)(ks * (256 >> 4));     // two k-cores of 128 bytes
+          mma_tf32<TN>(d, a_hi + o, b_hi + o, (g_first && ks == 0) ? 0u : 1u);
+          mma_tf32<TN>(d, a_hi + o, b_lo + o, 1u);
+          mma_tf32<TN>(d, a_lo + o, b_hi + o, 1u);
         }
         umma_commit(&op_empty[os]);
         if (g_last) umma_commit(&acc_full[g & 1]);
@@ -257,6 +270,16 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     };
     constexpr int ITEMS_A = TM / 8, ITEMS_B = TN / 8;          // warp-items per tile (32 (row, k-core) pairs each)
+    constexpr int NIT = (ITEMS_A + ITEMS_B) / G::NCW;          // items per warp and k-block (3 or 4); item i of warp cw is
+    static_assert((ITEMS_A + ITEMS_B) % G::NCW == 0 && ITEMS_A % G::NCW == 0, "items must divide evenly");   // cw + NCW*i
+    constexpr int NIT_A = ITEMS_A / G::NCW;                    // the first NIT_A items of a warp belong to A, the rest to B
+    int src_off[NIT], dst_off[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int wi = cw + G::NCW * i;
+      if (i < NIT_A) item_offsets<A_KC>(TM, wi, lane, &src_off[i], &dst_off[i]);
+      else item_offsets<B_KC>(TN, wi - ITEMS_A, lane, &src_off[i], &dst_off[i]);
+    }
     int drained = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int rs = kb % RAW_STAGES, os = kb % OP_STAGES, g = kb / GROUP_KB;
@@ -266,9 +289,10 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       const unsigned char* rb = ra + G::RAW_A;
       unsigned char* oa = op_ring + (size_t)os * G::OP_STAGE;
       unsigned char* ob = oa + 2 * G::OP_A;
-      for (int wi = cw; wi < ITEMS_A + ITEMS_B; wi += G::NCW) {
-        if (wi < ITEMS_A) convert_item<A_KC>(ra, TM, wi, lane, oa, oa + G::OP_A);
-        else convert_item<B_KC>(rb, TN, wi - ITEMS_A, lane, ob, ob + G::OP_B);
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        if (i < NIT_A) convert_item<A_KC, TM>(ra, src_off[i], dst_off[i], oa, oa + G::OP_A);
+        else convert_item<B_KC, TN>(rb, src_off[i], dst_off[i], ob, ob + G::OP_B);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       __syncwarp();
