@@ -398,6 +398,22 @@ def bench_pairwise(wl, args, eng, dev, barrier, clocks, with_extra=True):
         extra[f"{wl}_without_index_prefetch_triplets_per_sec"] = short(pipeline=False)
         if wl == "bpr":
             extra["bpr_sgd_triplets_per_sec"] = short(o=N.opt(N.ORX_OPT_SGD, LR))
+            # a Zipf(1.05) id distribution exposes duplicate contention (most lookups hit rows that other
+            # triplets of the batch also hit: they go through the staging buffer and the tail instead of the in-register
+            # update).  Ranks are shuffled over the row space so that hot rows are not neighbours.
+            zr = np.random.default_rng(5)
+            pk = np.arange(1, U + 1, dtype=np.float64) ** -1.05
+            pk /= pk.sum()
+            relabel = [zr.permutation(n).astype(np.int32) for n in (U, I)]
+            saved = list(dev_ids)
+            for k in range(N_BATCHES):
+                draws = [zr.choice(U, size=B, p=pk) for _ in range(3)]
+                dev_ids[k] = tuple(torch.from_numpy(relabel[min(j, 1)][d]).to(dev) for j, d in enumerate(draws))
+            torch.cuda.synchronize()
+            extra["bpr_zipf1.05_triplets_per_sec"] = short(pipeline=False)
+            u0 = dev_ids[0][0]
+            extra["bpr_zipf1.05_unique_user_rows_per_batch"] = int(torch.unique(u0).numel())
+            dev_ids[:] = saved
 
     # ---- e2e: public API (openrec.tf2 model + GradientTape + Adagrad), host ids in, loss out, every step
     sys.path.insert(0, os.path.join(ROOT, "compat"))

@@ -270,13 +270,31 @@ ORX_API int orx_score_all(orx_handle_t h, int32_t kind, const float* user_tab, i
                   const float* scale, const float* item_tab, const float* item_bias, int64_t I, int32_t dim,
                   float* scores, orx_stream_t s);
 
-/* ---- device-side pairwise sampler (semantics of openrec/tf2/data/dataset.py:7-16 +
- * data/utils.py:82-87,102-116): slot b takes record perm[(cursor+b) % n_records] and a uniform negative rejected while
- * it is one of that user's positives (csr_off[U+1] / csr_items sorted per user). */
-ORX_API int orx_sample_pairwise(orx_handle_t h, const int32_t* rec_user, const int32_t* rec_item, const int64_t* perm,
-                                int64_t cursor, int64_t n_records, const int64_t* csr_off, const int32_t* csr_items,
-                                int32_t total_items, uint64_t seed, int32_t B, int32_t* uid, int32_t* pid, int32_t* nid,
-                                orx_stream_t s);
+/* ---- device-side samplers (semantics of openrec/tf2/data/dataset.py:7-58 + data/utils.py:82-87,102-116).
+ * orx_sampler_t: the interaction records, the random permutations of the current and of the next epoch (records are
+ * consumed in permutation order and never dropped: a batch that crosses the end of an epoch continues in perm_next),
+ * `cursor` = records of the current epoch already consumed, and the users' positives as a CSR with sorted rows.
+ * Every draw is a pure function of (seed, stream_pos + slot): stream_pos = samples emitted before this batch.
+ *   orx_sample_pairwise     : slot b = record b from the cursor + one uniform negative rejected while positive for the user
+ *   orx_sample_stratified   : per slot a coin: the next record (label 1) with probability pos_ratio, else a uniform
+ *                             unobserved (user, item) pair (label 0); *n_pos_out (device) = records consumed by the batch
+ *   orx_sample_per_positive : the stream "record, then `quota` distinct items != its positive" cut at stream_pos; the
+ *                             cursor must point at the record of the group that contains stream_pos. */
+typedef struct {
+  const int32_t *rec_user, *rec_item;     /* [n_records] */
+  const int64_t *perm_cur, *perm_next;    /* [n_records] each */
+  int64_t cursor, n_records;
+  const int64_t* csr_off;                 /* [total_users + 1] */
+  const int32_t* csr_items;               /* [n_records], sorted inside each user's range */
+  int32_t total_users, total_items;
+} orx_sampler_t;
+ORX_API int orx_sample_pairwise(orx_handle_t h, const orx_sampler_t* sd_host, uint64_t seed, int64_t stream_pos, int32_t B,
+                                int32_t* uid, int32_t* pid, int32_t* nid, orx_stream_t s);
+ORX_API int orx_sample_stratified(orx_handle_t h, const orx_sampler_t* sd_host, uint64_t seed, int64_t stream_pos, int32_t B,
+                                  float pos_ratio, int32_t* uid, int32_t* iid, float* label, int32_t* n_pos_out,
+                                  orx_stream_t s);
+ORX_API int orx_sample_per_positive(orx_handle_t h, const orx_sampler_t* sd_host, uint64_t seed, int64_t stream_pos, int32_t B,
+                                    int32_t quota, int32_t* uid, int32_t* iid, float* label, orx_stream_t s);
 
 /* ---- ranking metrics (openrec/tf2/metrics/ranking_metrics.py:8-69), one row per user --------
  * pos/excl are uint8 masks [R, I]; at[] (host) the cut-offs; outputs auc[R], ndcg[R,n_at], recall[R,n_at]

@@ -35,6 +35,12 @@ class OrxShard(C.Structure):
                 ("gin", C.c_void_p), ("ginb", C.c_void_p), ("meta", C.c_void_p), ("flags", C.c_void_p)]
 
 
+class OrxSampler(C.Structure):
+    _fields_ = [("rec_user", C.c_void_p), ("rec_item", C.c_void_p), ("perm_cur", C.c_void_p), ("perm_next", C.c_void_p),
+                ("cursor", C.c_int64), ("n_records", C.c_int64), ("csr_off", C.c_void_p), ("csr_items", C.c_void_p),
+                ("total_users", C.c_int32), ("total_items", C.c_int32)]
+
+
 _vp, _i32, _i64, _f, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 _T = C.POINTER(OrxTable)
 _O = C.POINTER(OrxOpt)
@@ -86,7 +92,9 @@ SIGNATURES = {
                            _vp, _vp, _vp, _vp, _vp, _vp],
     "orx_dense_apply": [_vp, _vp, _vp, _vp, _vp, _i64, _O, _vp],
     "orx_score_all": [_vp, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp],
-    "orx_sample_pairwise": [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _u64, _i32, _vp, _vp, _vp, _vp],
+    "orx_sample_pairwise": [_vp, C.POINTER(OrxSampler), _u64, _i64, _i32, _vp, _vp, _vp, _vp],
+    "orx_sample_stratified": [_vp, C.POINTER(OrxSampler), _u64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _vp],
+    "orx_sample_per_positive": [_vp, C.POINTER(OrxSampler), _u64, _i64, _i32, _i32, _vp, _vp, _vp, _vp],
     "orx_rank_metrics": [_vp, _vp, _vp, _vp, _i32, _i64, C.POINTER(_i32), _i32, _vp, _vp, _vp, _vp],
 }
 

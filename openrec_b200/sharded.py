@@ -165,7 +165,7 @@ class HomeRoutedPairwise:
 
     def __init__(self, eng, rank, world, total_users, total_items, dim, batch, *, kind=0, opt_kind=1, lr=0.05, eps=1e-7,
                  beta1=0.9, beta2=0.999, margin=0.5, seed=0, init=True, home_cap=None, gin_cap=None, timeout_ms=20000,
-                 peers=None):
+                 peers=None, tables=None, slots=None):
         if dim % 4 or dim > 512:
             raise ValueError("the sharded step needs dim % 4 == 0 and dim <= 512")
         if opt_kind not in (0, 1, 2):
@@ -177,16 +177,25 @@ class HomeRoutedPairwise:
         dev = eng.device
         self.ru = (total_users - rank + world - 1) // world     # rows r with r % world == rank
         self.ri = (total_items - rank + world - 1) // world
-        self.user = torch.zeros(max(self.ru, 1), dim, dtype=torch.float32, device=dev)
-        self.item = torch.zeros(max(self.ri, 1), dim, dtype=torch.float32, device=dev)
-        self.bias = torch.zeros(max(self.ri, 1), 1, dtype=torch.float32, device=dev)
-        if init:
-            for k, t in enumerate((self.user, self.item, self.bias)):
-                eng.fill_uniform(t, -0.05, 0.05, seed * 1000003 + rank * 17 + k)
+        if tables is not None:          # shards owned by the caller (openrec.tf2.recommenders.ShardedBPR: keras variables)
+            self.user, self.item, self.bias = tables
+            want = ((max(self.ru, 1), dim), (max(self.ri, 1), dim), (max(self.ri, 1), 1))
+            if tuple(tuple(t.shape) for t in tables) != want:
+                raise ValueError(f"shard shapes {[tuple(t.shape) for t in tables]} != {want}")
+        else:
+            self.user = torch.zeros(max(self.ru, 1), dim, dtype=torch.float32, device=dev)
+            self.item = torch.zeros(max(self.ri, 1), dim, dtype=torch.float32, device=dev)
+            self.bias = torch.zeros(max(self.ri, 1), 1, dtype=torch.float32, device=dev)
+            if init:
+                for k, t in enumerate((self.user, self.item, self.bias)):
+                    eng.fill_uniform(t, -0.05, 0.05, seed * 1000003 + rank * 17 + k)
         n_slots = {0: 0, 1: 1, 2: 2}[opt_kind]
         fill = 0.1 if opt_kind == 1 else 0.0
         mk = lambda t: [torch.full_like(t, fill) for _ in range(n_slots)] + [None] * (2 - n_slots)
-        self.user_slots, self.item_slots, self.bias_slots = mk(self.user), mk(self.item), mk(self.bias)
+        if slots is not None:           # optimizer slots owned by the caller (the keras optimizer's slot tensors)
+            self.user_slots, self.item_slots, self.bias_slots = (list(x) for x in slots)
+        else:
+            self.user_slots, self.item_slots, self.bias_slots = mk(self.user), mk(self.item), mk(self.bias)
         # capacities: worst case for small problems (tests), 2x the expected load for big ones (errors are sticky flags)
         small = world * batch <= (1 << 16)
         self.home_cap = int(home_cap or (world * batch if small else 2 * batch))

@@ -5,8 +5,11 @@ from .dataset import Dataset
 __all__ = ["Dataset", "_DataStore", "_ParallelDataset"]
 
 
+_DEVICE = ("DevicePairwiseSampler", "DeviceStratifiedSampler", "DevicePerPositiveSampler")
+
+
 def __getattr__(name):   # lazy: keeps torch out of the spawned sampler workers
-    if name == "DevicePairwiseSampler":
-        from .device_sampler import DevicePairwiseSampler
-        return DevicePairwiseSampler
+    if name in _DEVICE:
+        from . import device_sampler
+        return getattr(device_sampler, name)
     raise AttributeError(name)

@@ -10,3 +10,10 @@ try:  # DLRM needs the MLP / interaction kernels
     __all__.append("DLRM")
 except ImportError:  # pragma: no cover
     pass
+
+
+def __getattr__(name):   # row-sharded BPR / UCML (torch.distributed): imported on demand
+    if name in ("ShardedBPR", "ShardedUCML"):
+        from . import sharded
+        return getattr(sharded, name)
+    raise AttributeError(name)

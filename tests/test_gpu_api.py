@@ -216,29 +216,85 @@ def test_example_flow_end_to_end():
     assert all(0.0 <= a <= 1.0 for a in aucs)
 
 
-def test_device_sampler_semantics(tf):
-    """DevicePairwiseSampler: every record exactly once per epoch, negatives never positive for the user."""
-    from openrec.tf2.data import Dataset, DevicePairwiseSampler
-    rng = np.random.default_rng(17)
-    U, I, n = 300, 500, 4000
+def _sampler_dataset(seed=17, U=300, I=500, n=4000):
+    from openrec.tf2.data import Dataset
+    rng = np.random.default_rng(seed)
     pairs = np.unique(np.stack([rng.integers(0, U, n), rng.integers(0, I, n)], 1), axis=0)
     raw = np.empty(len(pairs), dtype=[("user_id", np.int32), ("item_id", np.int32)])
     raw["user_id"], raw["item_id"] = pairs[:, 0], pairs[:, 1]
-    ds = Dataset(raw_data=raw, total_users=U, total_items=I)
-    pos = set(map(tuple, pairs.tolist()))
-    B = 512
-    n_batches = len(raw) // B
-    it = DevicePairwiseSampler(ds, batch_size=B, take=2 * n_batches + 1, seed=3)
-    seen = []
+    return Dataset(raw_data=raw, total_users=U, total_items=I), set(map(tuple, pairs.tolist())), len(raw), U, I
+
+
+def test_device_sampler_semantics(tf):
+    """DevicePairwiseSampler: every record exactly once per epoch -- batches that straddle the end of an epoch included,
+    nothing dropped (data/utils.py:82-87) -- and negatives are never positive for the user."""
+    from openrec.tf2.data import DevicePairwiseSampler
+    ds, pos, n, U, I = _sampler_dataset()
+    B = 500                                   # n is not a multiple of B: batches cross the epoch boundaries
+    assert n % B != 0
+    n_batches = (3 * n) // B
+    it = DevicePairwiseSampler(ds, batch_size=B, take=n_batches, seed=3)
+    stream = []
     for k, b in enumerate(it):
         u, p, q = (b[x].numpy() for x in ("user_id", "p_item_id", "n_item_id"))
         assert u.dtype == np.int32 and u.shape == (B,)
         assert all((int(a), int(c)) in pos for a, c in zip(u, p))          # positives are records
         assert not any((int(a), int(c)) in pos for a, c in zip(u, q))      # negatives are never positives
         assert q.min() >= 0 and q.max() < I
-        if k < n_batches:
-            seen += list(zip(u.tolist(), p.tolist()))
-    assert k == 2 * n_batches and len(set(seen)) == len(seen) == n_batches * B   # no repeats inside an epoch
+        stream += list(zip(u.tolist(), p.tolist()))
+    assert k == n_batches - 1
+    for e in range(len(stream) // n):                                      # every complete epoch = every record once
+        assert set(stream[e * n:(e + 1) * n]) == pos
+    assert len(set(stream[:n])) == n and stream[:n] != stream[n:2 * n]     # and a fresh permutation per epoch
+
+
+def test_device_stratified_sampler(tf):
+    """DeviceStratifiedSampler (dataset.py:18-34): label 1 = observed records in permutation order (each exactly once per
+    epoch, across batch boundaries), label 0 = unobserved pairs, fraction of positives ~ pos_ratio."""
+    from openrec.tf2.data import DeviceStratifiedSampler
+    ds, pos, n, U, I = _sampler_dataset(seed=18)
+    B, ratio = 700, 0.3
+    it = DeviceStratifiedSampler(ds, batch_size=B, pos_ratio=ratio, take=40, seed=5)
+    positives, n_lab1, total = [], 0, 0
+    for b in it:
+        u, i, lab = (b[x].numpy() for x in ("user_id", "item_id", "label"))
+        assert lab.dtype == np.float32 and set(np.unique(lab).tolist()) <= {0.0, 1.0}
+        for a, c, l in zip(u.tolist(), i.tolist(), lab.tolist()):
+            assert ((a, c) in pos) == (l == 1.0)
+        positives += [(a, c) for a, c, l in zip(u.tolist(), i.tolist(), lab.tolist()) if l == 1.0]
+        n_lab1 += int(lab.sum())
+        total += B
+    assert abs(n_lab1 / total - ratio) < 0.03
+    assert len(positives) > n                                              # more than one epoch of records was consumed
+    assert set(positives[:n]) == pos and len(set(positives[:n])) == n      # the first epoch: every record exactly once
+
+
+def test_device_per_positive_sampler(tf):
+    """DevicePerPositiveSampler (dataset.py:36-58): the stream record, quota distinct other items, record, ... cut into
+    batches at arbitrary positions; group content does not depend on where the cut falls."""
+    from openrec.tf2.data import DevicePerPositiveSampler
+    ds, pos, n, U, I = _sampler_dataset(seed=19, n=1500)
+    ratio, quota = 0.2, 4
+
+    def stream(B, batches):
+        out = []
+        for b in DevicePerPositiveSampler(ds, batch_size=B, pos_ratio=ratio, take=batches, seed=7):
+            out += list(zip(b["user_id"].numpy().tolist(), b["item_id"].numpy().tolist(), b["label"].numpy().tolist()))
+        return out
+    s1 = stream(333, 30)                       # 333 is not a multiple of the group size 5
+    s2 = stream(999, 10)
+    assert s1 == s2                            # same stream however it is batched
+    g = quota + 1
+    recs = []
+    for k in range(len(s1) // g):
+        grp = s1[k * g:(k + 1) * g]
+        u, p, l = grp[0]
+        assert l == 1.0 and (u, p) in pos
+        negs = [x[1] for x in grp[1:]]
+        assert all(x[0] == u and x[2] == 0.0 for x in grp[1:])
+        assert len(set(negs)) == quota and p not in negs and min(negs) >= 0 and max(negs) < I
+        recs.append((u, p))
+    assert len(recs) > n and set(recs[:n]) == pos and len(set(recs[:n])) == n
 
 
 def test_checkpoint_roundtrip(tf, tmp_path):
@@ -260,3 +316,46 @@ def test_checkpoint_roundtrip(tf, tmp_path):
     assert abs(float(l1[0]) - float(l2[0])) <= 1e-6 * abs(float(l1[0]))
     for a, b in zip(snapshot(m1), snapshot(m2)):
         np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7)   # fp32 RED order on shared rows is not fixed run to run
+
+
+def test_sharded_class_surface_single_rank(tf, tmp_path):
+    """openrec.tf2.recommenders.ShardedBPR keeps the BPR constructor and step protocol on row-sharded tables (here a
+    world of one rank, so the whole flow -- route, request, serve, compute, apply, tail, flag words -- runs on this GPU):
+    same losses and tables as the single-GPU BPR started from the same weights; shard checkpoint round trip."""
+    import torch.distributed as dist
+    from openrec.tf2.recommenders import BPR, ShardedBPR
+    from openrec_b200.tf2 import checkpoint
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{29700 + os.getpid() % 200}", rank=0, world_size=1)
+        created = True
+    try:
+        rng = np.random.default_rng(21)
+        U, I, D, B = 211, 307, 64, 512
+        ref = BPR(D, D, U, I)
+        sh = ShardedBPR(D, D, U, I)
+        for a, b in zip(sh.variables, ref.variables):
+            a.assign(b.numpy())
+        o_ref = tf.keras.optimizers.Adagrad(learning_rate=0.05)
+        o_sh = tf.keras.optimizers.Adagrad(learning_rate=0.05)
+        for step in range(3):
+            ids = make_ids(rng, U, I, B)
+            l_ref = train_step(tf, ref, o_ref, *ids)
+            l_sh = train_step(tf, sh, o_sh, *ids)
+            np.testing.assert_allclose(float(l_sh[0]), float(l_ref[0]), rtol=2e-5)
+            np.testing.assert_allclose(float(l_sh[1]), float(l_ref[1]), rtol=2e-5)
+        sh.check()
+        for a, b in zip(sh.variables, ref.variables):
+            np.testing.assert_allclose(a.numpy(), b.numpy(), atol=1e-6)
+        checkpoint.save(tmp_path / "shard0", sh, o_sh)
+        sh2 = ShardedBPR(D, D, U, I, seed=5)
+        o2 = tf.keras.optimizers.Adagrad(learning_rate=0.05)
+        checkpoint.load(tmp_path / "shard0", sh2, o2)
+        ids = make_ids(rng, U, I, B)
+        l1, l2 = train_step(tf, sh, o_sh, *ids), train_step(tf, sh2, o2, *ids)
+        np.testing.assert_allclose(float(l1[0]), float(l2[0]), rtol=1e-6)
+        with pytest.raises(NotImplementedError):
+            train_step(tf, ShardedBPR(D, D, U, I), tf.keras.optimizers.Adam(), *ids)
+    finally:
+        if created:
+            dist.destroy_process_group()

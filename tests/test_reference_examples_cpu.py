@@ -1,101 +1,35 @@
-"""CPU, build container only: the reference's tf2_examples/bpr_citeulike.py runs UNMODIFIED against
-openrec_b200's `openrec.tf2` + `tensorflow` surfaces (compat/).  The script is read from /root/reference
-(it may not be copied into this repo), fed synthetic CiteULike-shape files under ../dataset/, and the
-liborx engine is replaced by the oracle-backed stand-in of tests/fake_engine.py (no GPU here).  What this
-pins is the host side: import paths, constructor/kwarg surface, sampler workers, the GradientTape ->
-apply_gradients step protocol, evaluation generator, metrics, printing.  Skipped where /root/reference is
-absent (the GPU box); the same flow on the real kernels is tests/test_gpu_api.py::test_example_flow_end_to_end."""
+"""CPU, build container only: the reference's tf2_examples/bpr_citeulike.py and dlrm_criteo.py run UNMODIFIED against
+openrec_b200's `openrec.tf2` + `tensorflow` surfaces (compat/).  The scripts are read from /root/reference, fed synthetic
+files under ../dataset/, and the liborx engine is replaced by the oracle-backed stand-in of tests/fake_engine.py (no GPU
+here).  What this pins is the host side: import paths, constructor/kwarg surface, sampler workers, the GradientTape ->
+apply_gradients step protocol, evaluation generator, metrics, printing.  Skipped where /root/reference is absent; the same
+scripts on the real kernels: tests/test_gpu_reference_examples.py."""
 import os
-import signal
 import subprocess
 import sys
-import time
 
-import numpy as np
 import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from _examples_common import check_bpr_line, check_dlrm_line, make_citeulike, make_criteo, run_until, runner_code
+
 REF = "/root/reference/tf2_examples"
-
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
-
-RUNNER = r"""
-import sys, runpy
-sys.path[:0] = [{compat!r}, {root!r}, {tests!r}, {ref!r}]
-import fake_engine
-fake_engine.install()
-runpy.run_path({script!r}, run_name="__main__")
-"""
-
-
-def _run_until(cmd, cwd, needles, timeout):
-    p = subprocess.Popen(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, start_new_session=True)
-    os.set_blocking(p.stdout.fileno(), False)
-    buf, t0 = b"", time.time()
-    try:
-        while time.time() - t0 < timeout:
-            chunk = p.stdout.read()
-            if chunk:
-                buf += chunk
-            if all(n in buf for n in needles):
-                return buf.decode(errors="replace"), True
-            if p.poll() is not None:
-                break
-            time.sleep(0.2)
-        return buf.decode(errors="replace"), False
-    finally:
-        try:
-            os.killpg(p.pid, signal.SIGTERM)     # the script loops forever (total_iter is unused): stop our group
-        except ProcessLookupError:
-            pass
-        p.wait(timeout=30)
 
 
 def test_bpr_citeulike_runs_unmodified(tmp_path):
-    rng = np.random.default_rng(0)
-    U, I = 5551, 16980                                    # tf2_examples/dataloader.py:22-23
-    d = tmp_path / "dataset" / "citeulike"
-    d.mkdir(parents=True)
-    pairs = np.unique(np.stack([rng.integers(0, U, 30000), rng.integers(0, I, 30000)], 1), axis=0)
-    rng.shuffle(pairs)
-    raw = np.empty(len(pairs), dtype=[("user_id", np.int32), ("item_id", np.int32)])
-    raw["user_id"], raw["item_id"] = pairs[:, 0], pairs[:, 1]
-    np.save(d / "user_data_train.npy", raw[200:])
-    np.save(d / "user_data_val.npy", raw[:120])
-    np.save(d / "user_data_test.npy", raw[120:200])
-    work = tmp_path / "work"
-    work.mkdir()
-    code = RUNNER.format(compat=os.path.join(ROOT, "compat"), root=ROOT, tests=os.path.join(ROOT, "tests"), ref=REF,
-                         script=os.path.join(REF, "bpr_citeulike.py"))
-    out, ok = _run_until([sys.executable, "-c", code], str(work), [b"Iter: 0, Loss:", b"3 iter training."], 600)
+    work = make_citeulike(tmp_path)
+    out, ok = run_until([sys.executable, "-c", runner_code(REF, "bpr_citeulike.py", True)], str(work),
+                        [b"Iter: 0, Loss:", b"3 iter training."], 600)
     assert ok, out[-3000:]
-    line = [l for l in out.replace("\r", "\n").splitlines() if l.startswith("Iter: 0")][0]
-    loss = float(line.split("Loss:")[1].split(",")[0])
-    auc = float(line.split("AUC:")[1].split(",")[0])
-    # fresh U(-0.05,0.05) tables: BPR loss ~ log 2 = 0.69, l2 ~ 0.5*3000*50*(0.05^2/3) = 62.5; the script prints the
-    # mean of the two numbers => ~31.6
-    assert 29.0 < loss < 34.0 and 0.3 < auc < 0.7, line
+    check_bpr_line(out)
 
 
 def test_dlrm_criteo_runs_unmodified(tmp_path):
     """tf2_examples/dlrm_criteo.py: tf.data pipeline -> DLRM under GradientTape -> Adam -> keras AUC.
     The script makes one pass over its (here: small synthetic) training slice and exits by itself."""
-    rng = np.random.default_rng(1)
-    n = 24000
-    counts = rng.integers(3, 400, 26)
-    d = tmp_path / "dataset" / "criteo"
-    d.mkdir(parents=True)
-    np.savez(d / "kaggle_processed.npz", X_int=rng.integers(0, 100, (n, 13)), y=(rng.random(n) < 0.25).astype(np.int64),
-             X_cat=np.stack([rng.integers(0, c, n) for c in counts], 1), counts=counts)   # dataloader.py:50-55
-    work = tmp_path / "work"
-    work.mkdir()
-    code = RUNNER.format(compat=os.path.join(ROOT, "compat"), root=ROOT, tests=os.path.join(ROOT, "tests"), ref=REF,
-                         script=os.path.join(REF, "dlrm_criteo.py"))
-    r = subprocess.run([sys.executable, "-c", code], cwd=str(work), capture_output=True, text=True, timeout=900)
+    work = make_criteo(tmp_path)
+    r = subprocess.run([sys.executable, "-c", runner_code(REF, "dlrm_criteo.py", True)], cwd=str(work), capture_output=True,
+                       text=True, timeout=900)
     out = (r.stdout + r.stderr).replace("\r", "\n")
     assert r.returncode == 0, out[-3000:]
-    line = [l for l in out.splitlines() if l.startswith("Iter: 0")][0]
-    loss = float(line.split("Loss:")[1].split(",")[0])
-    auc = float(line.split("AUC:")[1])
-    # MSE of a ~0.5 sigmoid output against 25% positives; the reference's interaction is identically zero (Q1)
-    assert 0.15 < loss < 0.35 and 0.3 < auc < 0.7, line
+    check_dlrm_line(out)
