@@ -78,23 +78,53 @@ extern "C" int orx_gather(orx_handle_t h, const float* tab, int64_t rows, int32_
 // LatentFactor.censor (latent_factor.py:17-23), "K10": unique ids via the batch hash (the first
 // warp to insert an id owns the row), row <- row / max(||row||, min_norm).
 // ---------------------------------------------------------------------------------------
+// A warp takes 8 ids per iteration: lanes 0..7 load the ids and claim the rows in the hash in parallel, then (128-bit path)
+// all 8 rows are loaded before the first norm is reduced -- one row per warp left the kernel latency-bound (id -> hash ->
+// row -> reduce -> divide -> store: 23 us for 65 536 ids at D = 128, three of them per UCML step).
 __global__ void __launch_bounds__(256) k_censor(float* tab, int64_t rows, int D, const int32_t* __restrict__ ids,
                                                 int n, float min_norm, OrxHash hsh) {
   const int lane = threadIdx.x & 31;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= n) return;
-  const int32_t id = ids[b];
-  if (id < 0 || (int64_t)id >= rows) return;
-  uint32_t c = 0;
-  if (lane == 0) c = orx_hash_insert(hsh, id, 2);
-  c = __shfl_sync(ORX_FULL, c, 0);
-  if (c != 0u) return;  // another warp owns this row
-  float* row = tab + (int64_t)id * D;
-  float sq = 0.f;
-  for (int e = lane; e < D; e += 32) sq += row[e] * row[e];
-  sq = orx_group_sum<32>(sq);
-  const float den = fmaxf(sqrtf(sq), min_norm);
-  for (int e = lane; e < D; e += 32) row[e] = row[e] / den;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const bool vec = (D & 3) == 0 && D <= 128;
+  for (int b0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8; b0 < n; b0 += nw * 8) {
+    int32_t my_id = -1;
+    if (lane < 8 && b0 + lane < n) {
+      const int32_t id = ids[b0 + lane];
+      if (id >= 0 && (int64_t)id < rows && orx_hash_insert(hsh, id, 2) == 0u) my_id = id;   // first claim owns the row
+    }
+    if (vec) {
+      const int nq = D >> 2;
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int32_t id = __shfl_sync(ORX_FULL, my_id, k);
+        v[k] = (id >= 0 && lane < nq) ? __ldcg(reinterpret_cast<const float4*>(tab + (int64_t)id * D) + lane)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int32_t id = __shfl_sync(ORX_FULL, my_id, k);
+        if (id < 0) continue;
+        float sq = v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+        sq = orx_group_sum<32>(sq);
+        const float den = fmaxf(sqrtf(sq), min_norm);
+        if (lane < nq)
+          __stcg(reinterpret_cast<float4*>(tab + (int64_t)id * D) + lane,
+                 make_float4(v[k].x / den, v[k].y / den, v[k].z / den, v[k].w / den));
+      }
+    } else {
+      for (int k = 0; k < 8; ++k) {
+        const int32_t id = __shfl_sync(ORX_FULL, my_id, k);
+        if (id < 0) continue;
+        float* row = tab + (int64_t)id * D;
+        float sq = 0.f;
+        for (int e = lane; e < D; e += 32) sq += row[e] * row[e];
+        sq = orx_group_sum<32>(sq);
+        const float den = fmaxf(sqrtf(sq), min_norm);
+        for (int e = lane; e < D; e += 32) row[e] = row[e] / den;
+      }
+    }
+  }
 }
 
 extern "C" int orx_censor(orx_handle_t h, float* tab, int64_t rows, int32_t dim, const int32_t* ids, int32_t n,
@@ -107,7 +137,9 @@ extern "C" int orx_censor(orx_handle_t h, float* tab, int64_t rows, int32_t dim,
   int rc = orx_ensure_workspace(h, n, h->g_dim > 0 ? h->g_dim : 1, false);
   if (rc) return rc;
   if ((rc = orx_next_epoch(h, st))) return rc;   // the dedup hash needs no clearing: a new epoch empties it
-  k_censor<<<(n + 7) / 8, 256, 0, st>>>(tab, rows, dim, ids, n, min_norm, h->hu);
+  int blocks = (n + 63) / 64;                 // 8 warps x 8 ids per block and iteration
+  if (blocks > h->num_sms * 8) blocks = h->num_sms * 8;
+  k_censor<<<blocks, 256, 0, st>>>(tab, rows, dim, ids, n, min_norm, h->hu);
   ORX_LAUNCH_CHECK();
   return ORX_OK;
 }

@@ -496,71 +496,65 @@ __global__ void __launch_bounds__(256) k_sparse_tail(const TailArgs a) {
   const int nu = a.counters[0], ni = a.counters[1], nbad = a.counters[3];
   const int D = a.D;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  // Two staged rows per warp iteration: the tail is a chain of dependent round trips (staging index -> row id -> rows),
-  // so both rows' loads are issued before either is consumed.
-  for (int r = gwarp; r < nu + ni; r += 2 * nwarps) {
-    int rr[2] = {r, r + nwarps};
-    const bool two = rr[1] < nu + ni;
-    if (!two) rr[1] = r;
-    bool is_u[2];
-    int d[2], id[2];
+  // The tail is a chain of dependent round trips (counters -> row id -> rows) over a few thousand rows, i.e. latency,
+  // not bandwidth.  A warp therefore takes FOUR staged rows at once, eight lanes per row (a quarter-warp still covers
+  // 128 contiguous bytes per access), and issues all of a row's loads before the first use: 12 independent 128-bit
+  // loads per lane in flight at D = 128.
+  const int sub = lane >> 3, sl = lane & 7;
+  for (int r0 = gwarp * 4; r0 < nu + ni; r0 += nwarps * 4) {
+    const int r = r0 + sub;
+    const bool on = r < nu + ni;
+    const bool is_u = on && r < nu;
+    const int d = on ? (is_u ? r : r - nu) : 0;
+    const int id = on ? (is_u ? a.hu.did[d] : a.hi.did[d]) : 0;
+    float* G = (is_u ? a.gu : a.gi) + (int64_t)d * D;
+    float* W = (is_u ? a.U : a.I) + (int64_t)id * D;
+    float* P0 = (is_u ? a.Us0 : a.Is0) + (int64_t)id * D;
+    float* P1 = (is_u ? a.Us1 : a.Is1) + (int64_t)id * D;
+    if ((D & 3) == 0) {  // 128-bit path: float4 index sl + 8k
+      const int nq = D >> 2;
+      for (int e0 = 0; e0 < nq; e0 += 32) {
+        float4 g[4], w[4], s0v[4], s1v[4];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      is_u[k] = rr[k] < nu;
-      d[k] = is_u[k] ? rr[k] : rr[k] - nu;
-      id[k] = is_u[k] ? a.hu.did[d[k]] : a.hi.did[d[k]];
-    }
-    float *G[2], *W[2], *P0[2], *P1[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      G[k] = (is_u[k] ? a.gu : a.gi) + (int64_t)d[k] * D;
-      W[k] = (is_u[k] ? a.U : a.I) + (int64_t)id[k] * D;
-      P0[k] = (is_u[k] ? a.Us0 : a.Is0) + (int64_t)id[k] * D;
-      P1[k] = (is_u[k] ? a.Us1 : a.Is1) + (int64_t)id[k] * D;
-    }
-    if ((D & 3) == 0) {  // 128-bit path
-      for (int e = lane * 4; e < D; e += 128) {
-        float4 g[2], w[2], s0v[2], s1v[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const bool on = k == 0 || two;
-          g[k] = on ? __ldcg(reinterpret_cast<const float4*>(G[k] + e)) : z4;
-          w[k] = (on && !ZERO_ONLY) ? __ldcg(reinterpret_cast<const float4*>(W[k] + e)) : z4;
-          s0v[k] = (on && S0 && !ZERO_ONLY) ? __ldcg(reinterpret_cast<const float4*>(P0[k] + e)) : z4;
-          s1v[k] = (on && S1 && !ZERO_ONLY) ? __ldcg(reinterpret_cast<const float4*>(P1[k] + e)) : z4;
+        for (int k = 0; k < 4; ++k) {
+          const int e = e0 + sl + 8 * k;
+          const bool ld = on && e < nq;
+          g[k] = ld ? __ldcg(reinterpret_cast<const float4*>(G) + e) : z4;
+          w[k] = (ld && !ZERO_ONLY) ? __ldcg(reinterpret_cast<const float4*>(W) + e) : z4;
+          s0v[k] = (ld && S0 && !ZERO_ONLY) ? __ldcg(reinterpret_cast<const float4*>(P0) + e) : z4;
+          s1v[k] = (ld && S1 && !ZERO_ONLY) ? __ldcg(reinterpret_cast<const float4*>(P1) + e) : z4;
         }
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          if (k == 1 && !two) break;
+        for (int k = 0; k < 4; ++k) {
+          const int e = e0 + sl + 8 * k;
+          if (!on || e >= nq) continue;
           if (!ZERO_ONLY) {
-            __stcg(reinterpret_cast<float4*>(W[k] + e), orx_apply4<OPT>(w[k], g[k], s0v[k], s1v[k], a.opt));
-            if (S0) __stcg(reinterpret_cast<float4*>(P0[k] + e), s0v[k]);
-            if (S1) __stcg(reinterpret_cast<float4*>(P1[k] + e), s1v[k]);
+            __stcg(reinterpret_cast<float4*>(W) + e, orx_apply4<OPT>(w[k], g[k], s0v[k], s1v[k], a.opt));
+            if (S0) __stcg(reinterpret_cast<float4*>(P0) + e, s0v[k]);
+            if (S1) __stcg(reinterpret_cast<float4*>(P1) + e, s1v[k]);
           }
-          __stcg(reinterpret_cast<float4*>(G[k] + e), z4);
+          __stcg(reinterpret_cast<float4*>(G) + e, z4);
         }
       }
-    } else {
-      for (int k = 0; k < (two ? 2 : 1); ++k)
-        for (int e = lane; e < D; e += 32) {
-          if (!ZERO_ONLY) {
-            float s0v = S0 ? P0[k][e] : 0.f, s1v = S1 ? P1[k][e] : 0.f;
-            W[k][e] = orx_apply<OPT>(W[k][e], G[k][e], s0v, s1v, a.opt);
-            if (S0) P0[k][e] = s0v;
-            if (S1) P1[k][e] = s1v;
-          }
-          G[k][e] = 0.f;
+    } else if (on) {
+      for (int e = sl; e < D; e += 8) {
+        if (!ZERO_ONLY) {
+          float s0v = S0 ? P0[e] : 0.f, s1v = S1 ? P1[e] : 0.f;
+          W[e] = orx_apply<OPT>(W[e], G[e], s0v, s1v, a.opt);
+          if (S0) P0[e] = s0v;
+          if (S1) P1[e] = s1v;
         }
+        G[e] = 0.f;
+      }
     }
-    if (lane < (two ? 2 : 1) && !is_u[lane]) {     // lane k: the item bias of staged row k
-      const int k = lane, ib = id[k], db = d[k];
+    if (on && !is_u && sl == 0) {     // the item bias of the staged row
       if (!ZERO_ONLY) {
-        float s0v = S0 ? a.Bs0[ib] : 0.f, s1v = S1 ? a.Bs1[ib] : 0.f;
-        a.Bv[ib] = orx_apply<OPT>(a.Bv[ib], a.gb[db], s0v, s1v, a.opt);
-        if (S0) a.Bs0[ib] = s0v;
-        if (S1) a.Bs1[ib] = s1v;
+        float s0v = S0 ? a.Bs0[id] : 0.f, s1v = S1 ? a.Bs1[id] : 0.f;
+        a.Bv[id] = orx_apply<OPT>(a.Bv[id], a.gb[d], s0v, s1v, a.opt);
+        if (S0) a.Bs0[id] = s0v;
+        if (S1) a.Bs1[id] = s1v;
       }
-      a.gb[db] = 0.f;
+      a.gb[d] = 0.f;
     }
   }
   // (the hash tables are not cleared: the next step uses a new epoch)

@@ -31,21 +31,25 @@ class GemmProfile:
     def __exit__(self, *a):
         GemmProfile.active = None
 
-    def bracket(self, flops):
+    def bracket(self, flops, pure=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        self.ev.append((e0, e1, flops))
+        self.ev.append((e0, e1, flops, pure))
         return e0, e1
 
-    def totals(self):
+    def totals(self, pure_only=False):
+        """(ms, flops, calls) over all bracketed Dense-layer calls, or only over the calls that are ONE tcgen05 GEMM
+        launch (forward layers on the tensor-core path: bias + activation are fused into the GEMM's epilogue)."""
         torch.cuda.synchronize()
-        return (sum(a.elapsed_time(b) for a, b, _ in self.ev), float(sum(f for _, _, f in self.ev)), len(self.ev))
+        ev = [e for e in self.ev if e[3]] if pure_only else self.ev
+        return (sum(a.elapsed_time(b) for a, b, _, _ in ev), float(sum(f for _, _, f, _ in ev)), len(ev))
 
 
 def _mlp_fwd(eng, x, w, b, act, y):
     p = GemmProfile.active
     if p is None:
         return eng.mlp_fwd(x, w, b, act, y)
-    e0, e1 = p.bracket(2.0 * x.shape[0] * w.shape[0] * w.shape[1])
+    tc = x.shape[0] >= 64 and w.shape[0] >= 8 and w.shape[1] >= 16 and x.stride(0) % 4 == 0   # orx_launch_gemm_tc's rule
+    e0, e1 = p.bracket(2.0 * x.shape[0] * w.shape[0] * w.shape[1], pure=tc)
     e0.record()
     eng.mlp_fwd(x, w, b, act, y)
     e1.record()
