@@ -212,6 +212,10 @@ ORX_API int orx_pairwise_grad_rows(orx_handle_t h, int32_t kind, const float* ro
  *   (no barrier launches, no collective, nothing returns to the host).  user/item/item_bias are this rank's LOCAL shards.
  *   epoch: strictly increasing per step, starting at 1.  phase_lo..phase_hi (0..5) selects a sub-range of the launches so
  *   that several virtual ranks can be stepped phase by phase on one device (the 1-GPU loopback test).
+ *   next_uid / next_pid / next_nid / next_B (all NULL / 0, or all set: device pointers that stay valid until that step
+ *   ran) announce the batch of step epoch + 1: its route and request then ride inside this step's apply launch, and the
+ *   call for epoch + 1 -- which must pass exactly these pointers as uid / pid / nid -- issues four launches instead of six.
+ *   All ranks announce, or none.
  *   out4 = { loss, l2_loss (GLOBAL batch, identical on every rank), skipped triplets of this rank, staged rows }.
  *   The sticky error word flags[4*64] is 0 or: 1 a peer never arrived within timeout_ms, 2 more triplets routed to this
  *   home than home_cap, 3 / 4 request / gradient inbox too small.  SGD, Adagrad and row-sparse Adam. */
@@ -226,7 +230,8 @@ ORX_API int orx_peer_free(orx_handle_t h, void* dev_ptr);
 ORX_API int orx_shard_sizes(const orx_shard_t* x_host, int64_t* n8_host);
 ORX_API int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x_host, const orx_table_t* user,
                            const orx_table_t* item, const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid,
-                           const int32_t* nid, int32_t B, int64_t total_users, int64_t total_items, float margin,
+                           const int32_t* nid, int32_t B, const int32_t* next_uid, const int32_t* next_pid,
+                           const int32_t* next_nid, int32_t next_B, int64_t total_users, int64_t total_items, float margin,
                            float c_loss, float c_l2, float inv_B, const orx_opt_t* opt_host, int32_t epoch,
                            int32_t phase_lo, int32_t phase_hi, float* out4, orx_stream_t s);
 /* ---- dense variables (GMF w, MLP kernels/biases): Keras dense apply ---------------------- */

@@ -81,8 +81,8 @@ SIGNATURES = {
     "orx_peer_close": [_vp, _vp],
     "orx_peer_free": [_vp, _vp],
     "orx_shard_sizes": [_S, C.POINTER(_i64)],
-    "orx_shard_step": [_vp, _i32, _S, _T, _T, _T, _vp, _vp, _vp, _i32, _i64, _i64, _f, _f, _f, _f, _O, _i32, _i32, _i32,
-                       _vp, _vp],
+    "orx_shard_step": [_vp, _i32, _S, _T, _T, _T, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i64, _f, _f, _f, _f, _O,
+                       _i32, _i32, _i32, _vp, _vp],
     "orx_owner_bucket_combined": [_vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
     "orx_pairwise_grad_rows": [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _f, _f, _f, _f, _vp, _vp, _vp],
     "orx_owner_bucket": [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp],

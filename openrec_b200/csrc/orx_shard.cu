@@ -30,6 +30,11 @@
 // the rank's own k_sh_serve on the stream; user rows are read and written by the one triplet that owns them, shared ones
 // only in k_sh_tail.  Mailbox reuse across steps needs no extra synchronisation (proof per buffer in DESIGN.md 7).
 //
+// Prologue: a caller that announces the NEXT batch (next_uid / next_pid / next_nid of orx_shard_step) gets that step's
+// route and request as two extra block roles inside THIS step's k_sh_apply launch: two of the four cross-rank handoffs of
+// a step -- ~20-35 us each of launch, fence and flag latency with no bandwidth behind them -- run under the HBM-bound
+// apply, and the announced step is four launches (serve, compute, apply, tail).  Safety per buffer at ShProArgs.
+//
 // phase_lo / phase_hi of orx_shard_step select a sub-range of the six launches, so that R "virtual ranks" can share ONE
 // device and ONE stream (tests/test_gpu_shard_loopback.py): phase k is issued for every rank before phase k + 1, every
 // flag is already set when its consumer runs, and the exact kernels of the multi-GPU step are exercised on a 1-GPU box.
@@ -54,8 +59,8 @@ enum { SH_M_TRIPS = 0,    // triplets r routed to X                             
 
 // local control words (ShardWs::ctl)
 enum { SH_C_CURH = 0, SH_C_CURO = SH_MAX_R, SH_C_GOFF = 2 * SH_MAX_R, SH_C_RCO = 3 * SH_MAX_R + 1,
-       SH_C_DONE = 4 * SH_MAX_R + 1, SH_C_T = SH_C_DONE + 8, SH_C_NREQ = SH_C_T + 1, SH_C_BAD = SH_C_T + 2,
-       SH_C_WORDS = SH_C_T + 8 };
+       SH_C_DONE = 4 * SH_MAX_R + 1, SH_C_T = SH_C_DONE + 8, SH_C_NREQ = SH_C_T + 1, SH_C_ACUR = SH_C_T + 2,
+       SH_C_BAD = SH_C_T + 4 /* + step parity */, SH_C_WORDS = SH_C_T + 8 };
 
 struct ShardHost {   // mirrors orx_shard_t (include/orx.h)
   int32_t world, rank, dim, batch_cap, home_cap, req_cap, gin_cap, timeout_ms;
@@ -148,12 +153,12 @@ __device__ __forceinline__ void sh_wait(const ShardDev& x, int phase, int epoch)
 // causality order is transitive over morally-strong edges of different scopes), so a peer that acquires the flag sees
 // every block's stores.  A system fence per block cost ~5 us at the end of every launch (profiles/r2g).
 template <typename F>
-__device__ __forceinline__ void sh_arrive(const ShardDev& x, int32_t* done, int phase, int epoch, F publish) {
+__device__ __forceinline__ void sh_arrive(const ShardDev& x, int32_t* done, int nblk, int phase, int epoch, F publish) {
   __shared__ bool sh_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();                            // this block's stores are ordered before its ticket (GPU scope)
-    sh_last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
+    sh_last = (atomicAdd(done, 1) == nblk - 1);
     __threadfence();
   }
   __syncthreads();
@@ -169,32 +174,37 @@ __device__ __forceinline__ void sh_arrive(const ShardDev& x, int32_t* done, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 0: triplets -> homes
+// phase 0: triplets -> homes.  A "role": the body of k_sh_route, and of the first blocks of the PREVIOUS step's k_sh_apply
+// when the caller announced this batch there (see "prologue" in the file header).  bid / nblk = this block among the
+// role's blocks; par = step parity (epoch & 1) of the skipped-triplet counter.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sh_route(ShardDev x, ShardWs w, const int32_t* __restrict__ uid,
-                                                  const int32_t* __restrict__ pid, const int32_t* __restrict__ nid,
-                                                  int B, int64_t U, int64_t I, int epoch) {
+struct ShRouteArgs {
+  const int32_t *uid, *pid, *nid;
+  int B;
+  int64_t U, I;
+};
+
+__device__ __forceinline__ void sh_route_role(const ShardDev& x, const ShardWs& w, const ShRouteArgs& r, int epoch, int bid, int nblk) {
   __shared__ int32_t cnt[SH_MAX_R], base[SH_MAX_R];
   const int R = x.world;
   if ((int)threadIdx.x < R) cnt[threadIdx.x] = 0;
-  orx_pdl_wait();
   __syncthreads();
   int h[4], rk[4];
   int32_t uu[4], pp[4], nn[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int i = blockIdx.x * 1024 + k * 256 + threadIdx.x;
+    const int i = bid * 1024 + k * 256 + threadIdx.x;
     h[k] = -1;
     bool ok = false;
-    if (i < B) {
-      const int32_t u = uid[i], p = pid[i], n = nid[i];
+    if (i < r.B) {
+      const int32_t u = r.uid[i], p = r.pid[i], n = r.nid[i];
       // a triplet with ANY id out of range is skipped as a whole, like the single-GPU step (orx_pairwise.cu)
-      ok = u >= 0 && (int64_t)u < U && p >= 0 && (int64_t)p < I && n >= 0 && (int64_t)n < I;
+      ok = u >= 0 && (int64_t)u < r.U && p >= 0 && (int64_t)p < r.I && n >= 0 && (int64_t)n < r.I;
       if (ok) {
         h[k] = u % R;
         uu[k] = u / R; pp[k] = p; nn[k] = n;
       } else {
-        atomicAdd(w.ctl + SH_C_BAD, 1);
+        atomicAdd(w.ctl + SH_C_BAD + (epoch & 1), 1);
       }
     }
     rk[k] = sh_rank_add(cnt, ok ? h[k] : 0, ok);
@@ -211,24 +221,28 @@ __global__ void __launch_bounds__(256) k_sh_route(ShardDev x, ShardWs w, const i
     box[x.batch_cap + idx] = pp[k];
     box[2 * x.batch_cap + idx] = nn[k];
   }
-  orx_pdl_trigger();
-  sh_arrive(x, w.ctl + SH_C_DONE + 0, 0, epoch, [&]() {
+  sh_arrive(x, w.ctl + SH_C_DONE + 0, nblk, 0, epoch, [&]() {
     if ((int)threadIdx.x < R) {
-      const int r = threadIdx.x;
-      x.meta[r][SH_META * x.rank + SH_M_TRIPS] = __ldcg(w.ctl + SH_C_CURH + r);
-      w.ctl[SH_C_CURH + r] = 0;
+      const int q = threadIdx.x;
+      x.meta[q][SH_META * x.rank + SH_M_TRIPS] = __ldcg(w.ctl + SH_C_CURH + q);
+      w.ctl[SH_C_CURH + q] = 0;
     }
   });
 }
 
+__global__ void __launch_bounds__(256) k_sh_route(ShardDev x, ShardWs w, ShRouteArgs r, int epoch) {
+  orx_pdl_wait();
+  sh_route_role(x, w, r, epoch, blockIdx.x, gridDim.x);
+  orx_pdl_trigger();
+}
+
 // ---------------------------------------------------------------------------------------
-// phase 1: home: index my user rows, item lookups -> owners
+// phase 1: home: index my user rows, item lookups -> owners (a role, like phase 0)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHash hu, int epoch) {
+__device__ __forceinline__ void sh_request_role(const ShardDev& x, const ShardWs& w, const OrxHash& hu, int epoch, int bid, int nblk) {
   __shared__ int32_t toff[SH_MAX_R + 1], cnt[SH_MAX_R], base[SH_MAX_R], goff[SH_MAX_R + 1];
   __shared__ int T_sh;
   const int R = x.world, me = x.rank;
-  orx_pdl_wait();
   sh_wait(x, 0, epoch);
   if (threadIdx.x == 0) {
     const int32_t* m = x.meta[me];
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHa
   __syncthreads();
   const int T = T_sh;
   const int32_t* box = x.tripbox[me];
-  for (int c0 = blockIdx.x * 512; c0 < T; c0 += gridDim.x * 512) {
+  for (int c0 = bid * 512; c0 < T; c0 += nblk * 512) {
     if ((int)threadIdx.x < R) cnt[threadIdx.x] = 0;
     __syncthreads();
     int o[4], rk[4];
@@ -291,8 +305,7 @@ __global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHa
     }
     __syncthreads();
   }
-  orx_pdl_trigger();
-  sh_arrive(x, w.ctl + SH_C_DONE + 1, 1, epoch, [&]() {
+  sh_arrive(x, w.ctl + SH_C_DONE + 1, nblk, 1, epoch, [&]() {
     if (threadIdx.x == 0) {
       int acc = 0;
       for (int r = 0; r < R; ++r) {
@@ -314,6 +327,12 @@ __global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHa
       m[SH_M_GOTOFF] = goff[r];
     }
   });
+}
+
+__global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHash hu, int epoch) {
+  orx_pdl_wait();
+  sh_request_role(x, w, hu, epoch, blockIdx.x, gridDim.x);
+  orx_pdl_trigger();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -403,7 +422,7 @@ __global__ void __launch_bounds__(256) k_sh_serve(ShardDev x, ShardWs w, const f
     }
   }
   orx_pdl_trigger();
-  sh_arrive(x, w.ctl + SH_C_DONE + 2, 2, epoch, [&]() {});
+  sh_arrive(x, w.ctl + SH_C_DONE + 2, gridDim.x, 2, epoch, [&]() {});
 }
 
 // ---------------------------------------------------------------------------------------
@@ -553,7 +572,7 @@ __global__ void __launch_bounds__(256) k_sh_compute(ShardDev x, ShardWs w, ShCom
   }
   // The LAST block to finish reduces this rank's (loss, l2) partials, sends the pair to every rank and releases flag 3.
   __shared__ double sh_red[2][256];
-  sh_arrive(x, w.ctl + SH_C_DONE + 3, 3, epoch, [&]() {
+  sh_arrive(x, w.ctl + SH_C_DONE + 3, gridDim.x, 3, epoch, [&]() {
     double l = 0.0, q = 0.0;                           // deterministic (fixed order, double) reduction of my partials
     const int np = (int)((gridDim.x * blockDim.x) >> 5);
     for (int i = threadIdx.x; i < np; i += blockDim.x) {
@@ -589,21 +608,51 @@ struct ShApplyArgs {
   OrxOptDev opt;
 };
 
+// The prologue of the NEXT step (its route and request roles) rides in the first blocks of this launch when the caller
+// announced the next batch: apply is HBM-bound and needs no NVLink, the two roles are short and latency-bound (two
+// cross-rank handoffs), so they hide completely under it.  What they write is dead or private by now: tripbox / idbox /
+// the TRIPS, REQS and GOTOFF meta words were last read by request / serve of THIS step, which every rank finished before
+// any rank's compute -- and so before any rank's apply -- could start; trip_u / slot / the control words were last read
+// by this rank's compute; the user index of the next step is a second hash set (tail of this step still reads this one).
+struct ShProArgs {
+  int n_route, n_request;   // blocks of each role (0 = no prologue in this launch)
+  int epoch;                // of the announced step
+  ShRouteArgs r;
+  OrxHash hu;               // user index of the announced step
+};
+
 template <int OPT, int NQ>
-__global__ void __launch_bounds__(256) k_sh_apply(ShardDev x, ShardWs w, ShApplyArgs a, int epoch) {
+__global__ void __launch_bounds__(256) k_sh_apply(ShardDev x, ShardWs w, ShApplyArgs a, ShProArgs pro, int epoch) {
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   constexpr int GRP = NQ == 1 ? 4 : (NQ == 2 ? 2 : 1);   // rows whose loads are issued together
   const int me = x.rank, D = x.D, nq = D >> 2;
   orx_pdl_wait();
+  if ((int)blockIdx.x < pro.n_route) {                    // block-uniform role dispatch
+    sh_route_role(x, w, pro.r, pro.epoch, blockIdx.x, pro.n_route);
+    orx_pdl_trigger();
+    return;
+  }
+  if ((int)blockIdx.x < pro.n_route + pro.n_request) {
+    sh_request_role(x, w, pro.hu, pro.epoch, blockIdx.x - pro.n_route, pro.n_request);
+    orx_pdl_trigger();
+    return;
+  }
   sh_wait(x, 3, epoch);
   const int n = w.ctl[SH_C_NREQ];
-  const int lane = threadIdx.x & 31;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float* gin = x.gin[me];
   const float* ginb = x.ginb[me];
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8; j0 < n; j0 += nw * 8) {
+  __shared__ int chunk_sh;
+  // 64-row chunks handed out by a counter: blocks that start late (behind the prologue blocks) just take fewer chunks
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_sh = atomicAdd(w.ctl + SH_C_ACUR, 1);
+    __syncthreads();
+    const int j0 = chunk_sh * 64 + wid * 8;
+    if (chunk_sh * 64 >= n) break;
+    if (j0 >= n) continue;
     int32_t my_id = -1;
     int my_d = -1, my_own = 0;
     if (lane < 8) {
@@ -700,15 +749,15 @@ __device__ __forceinline__ void sh_apply_staged2(float* W, float* P0, float* P1,
 }
 
 template <int OPT>
-__global__ void __launch_bounds__(256) k_sh_tail(ShardDev x, ShardWs w, ShTailArgs u, ShApplyArgs a, int32_t* counters,
-                                                 float* out4) {
+__global__ void __launch_bounds__(256) k_sh_tail(ShardDev x, ShardWs w, ShTailArgs u, ShApplyArgs a, int32_t* ticket,
+                                                 int par, float* out4) {
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   const int D = x.D;
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   orx_pdl_wait();
-  const int nu = counters[0], ni = counters[1];
+  const int nu = *u.hu.counter, ni = *a.hi.counter;
   for (int r = gwarp; r < nu; r += 2 * nw) {
     const int r2 = r + nw;
     const bool two = r2 < nu;
@@ -737,18 +786,23 @@ __global__ void __launch_bounds__(256) k_sh_tail(ShardDev x, ShardWs w, ShTailAr
     }
     out4[0] = l;
     out4[1] = q;
-    out4[2] = (float)w.ctl[SH_C_BAD];
+    out4[2] = (float)w.ctl[SH_C_BAD + par];
     out4[3] = (float)(nu + ni);
-    w.ctl[SH_C_BAD] = 0;
+    w.ctl[SH_C_BAD + par] = 0;
+    w.ctl[SH_C_ACUR] = 0;
   }
   __shared__ bool last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    last = (atomicAdd(counters + 2, 1) == (int)gridDim.x - 1);
+    last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x < 4) counters[threadIdx.x] = 0;
+  if (last && threadIdx.x == 0) {
+    *u.hu.counter = 0;
+    *a.hi.counter = 0;
+    *ticket = 0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -757,6 +811,12 @@ __global__ void __launch_bounds__(256) k_sh_tail(ShardDev x, ShardWs w, ShTailAr
 struct orx_shard_ws {
   ShardWs w;
   int home_cap, gin_cap, got_rows;
+  // prologue bookkeeping, per step parity: which step's route / request were issued, with which index epochs and ids
+  int32_t pro_route[2], pro_request[2];
+  uint32_t ep_u[2], ep_i[2];
+  const int32_t *ids_u[2], *ids_p[2], *ids_n[2];
+  int32_t ids_B[2];
+  int32_t serve_epoch, tail_epoch;   // last step whose serve / tail was issued (different = a step's item index is live)
 };
 
 // ---- IPC-exportable device memory: every rank maps every other rank's mailboxes (cudaIpc*, one box, NVLink) ----
@@ -895,23 +955,49 @@ static int launch_compute(int nq, int num_sms, cudaStream_t st, const ShardDev& 
 #undef SH_GO
 }
 template <int OPT>
-static void launch_apply(int nq, int num_sms, cudaStream_t st, const ShardDev& xd, const ShardWs& w, const ShApplyArgs& a, int epoch) {
-#define SH_GO(NQ)                                                                   \
-  {                                                                                 \
-    const int g = num_sms * sh_ctas_per_sm((const void*)k_sh_apply<OPT, NQ>, 4);    \
-    orx_launch_pdl(k_sh_apply<OPT, NQ>, dim3(g), dim3(256), 0, st, xd, w, a, epoch); \
+static void launch_apply(int nq, int num_sms, cudaStream_t st, const ShardDev& xd, const ShardWs& w, const ShApplyArgs& a,
+                         const ShProArgs& pro, int epoch) {
+#define SH_GO(NQ)                                                                          \
+  {                                                                                        \
+    const int g = num_sms * sh_ctas_per_sm((const void*)k_sh_apply<OPT, NQ>, 4) + pro.n_route + pro.n_request; \
+    orx_launch_pdl(k_sh_apply<OPT, NQ>, dim3(g), dim3(256), 0, st, xd, w, a, pro, epoch);  \
   }
   if (nq <= 32) SH_GO(1) else if (nq <= 64) SH_GO(2) else SH_GO(4)
 #undef SH_GO
 }
 
-// One step (or a sub-range of its six launches: phases 0 route, 1 request, 2 serve, 3 compute, 4 apply, 5 tail).  See the file header.  out4 = { loss, l2_loss, skipped triplets (ids out of range), staged rows }, the
-// first two GLOBAL and identical on every rank.
+// two fresh index epochs (user set of the step, item set of the step).  A 31-bit wrap empties every table of the handle
+// after draining the device (orx_next_epoch), which must not happen while another step's index is live: `may_drain` says
+// whether it may; returns 1 (and takes nothing) when it may not and the wrap is near.
+static int shard_take_epochs(orx_ctx* c, cudaStream_t st, bool may_drain, uint32_t* eu, uint32_t* ei) {
+  if (c->epoch >= 0x7ffffff0u) {
+    if (!may_drain) return 1;
+    c->epoch = 0x7fffffffu;      // wrap now, at a step boundary: both epochs come from after the wrap
+  }
+  int rc;
+  if ((rc = orx_next_epoch(c, st))) return rc;
+  *eu = c->epoch;
+  if ((rc = orx_next_epoch(c, st))) return rc;
+  *ei = c->epoch;
+  return ORX_OK;
+}
+
+// One step (or a sub-range of its six launches: phases 0 route, 1 request, 2 serve, 3 compute, 4 apply, 5 tail); see the
+// file header.  out4 = { loss, l2_loss, skipped triplets (ids out of range), staged rows }, the first two GLOBAL and
+// identical on every rank.
+//
+// next_uid / next_pid / next_nid / next_B (all-or-none, device pointers that stay valid until that step ran) ANNOUNCE the
+// batch of step epoch + 1: its route and request ride inside this step's apply launch (ShProArgs), and the call for
+// epoch + 1 -- which must pass exactly these pointers -- starts at serve.  Every rank must announce or none (a rank that
+// does not would have its peers' next request wait for a route that comes a step later: slower, not wrong).
+// Phases 0 and 1 of a step may also be issued explicitly ahead of phases 4 and 5 of the step before (the 1-GPU loopback
+// does: fused roles of R virtual ranks on one stream would wait for each other).
 extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* xs, const orx_table_t* user,
                               const orx_table_t* item, const orx_table_t* item_bias, const int32_t* uid, const int32_t* pid,
-                              const int32_t* nid, int32_t B, int64_t total_users, int64_t total_items, float margin, float c_loss,
-                              float c_l2, float inv_B, const orx_opt_t* opt, int32_t epoch, int32_t phase_lo, int32_t phase_hi,
-                              float* out4, orx_stream_t s) {
+                              const int32_t* nid, int32_t B, const int32_t* next_uid, const int32_t* next_pid,
+                              const int32_t* next_nid, int32_t next_B, int64_t total_users, int64_t total_items, float margin,
+                              float c_loss, float c_l2, float inv_B, const orx_opt_t* opt, int32_t epoch, int32_t phase_lo,
+                              int32_t phase_hi, float* out4, orx_stream_t s) {
   const ShardHost* x = (const ShardHost*)xs;
   int rc = shard_check(h, x);
   if (rc) return rc;
@@ -919,7 +1005,10 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
   ORX_REQUIRE(user && item && item_bias && user->var && item->var && item_bias->var && opt && out4, "null pointer");
   ORX_REQUIRE(user->dim == x->dim && item->dim == x->dim && item_bias->dim == 1 && item_bias->rows == item->rows, "table shapes");
   ORX_REQUIRE(B > 0 && B <= x->batch_cap && uid && pid && nid, "bad batch (larger than the mailboxes were built for?)");
-  ORX_REQUIRE(total_users > 0 && total_items > 0 && epoch > 0, "bad totals / epoch");
+  const bool announce = next_uid != nullptr;
+  ORX_REQUIRE(announce == (next_pid != nullptr) && announce == (next_nid != nullptr), "next_uid / next_pid / next_nid: all or none");
+  if (announce) ORX_REQUIRE(next_B > 0 && next_B <= x->batch_cap, "bad announced batch");
+  ORX_REQUIRE(total_users > 0 && total_items > 0 && epoch > 0 && epoch < 0x7ffffffe, "bad totals / epoch");
   ORX_REQUIRE(phase_lo >= 0 && phase_hi <= 5 && phase_lo <= phase_hi, "bad phase range");
   ORX_REQUIRE(opt->kind == ORX_OPT_SGD || opt->kind == ORX_OPT_ADAGRAD || opt->kind == ORX_OPT_ADAM_LAZY,
               "the sharded step supports SGD, Adagrad and row-sparse Adam");
@@ -931,42 +1020,68 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
   const int64_t need = x->home_cap > (x->gin_cap + 1) / 2 ? x->home_cap : (x->gin_cap + 1) / 2;
   if ((rc = orx_ensure_workspace(h, need, x->dim, false))) return rc;
   if ((rc = shard_ws_ensure(h, x, st))) return rc;
-  const ShardWs& w = ((orx_shard_ws*)h->shard_ws)->w;
+  orx_shard_ws* S = (orx_shard_ws*)h->shard_ws;
+  const ShardWs& w = S->w;
   const ShardDev xd = shard_to_dev(x);
-  if (phase_lo == 0)
-    if ((rc = orx_next_epoch(h, st))) return rc;
+  const int par = epoch & 1;
   const OrxOptDev od = orx_opt_to_dev(opt);
   const int nq = x->dim >> 2;
   if ((rc = orx_ensure_partials(h, h->num_sms * 4 * 8, st))) return rc;   // compute grid <= 4 CTAs/SM x 8 warps
+  const int route_blocks = (B + 1023) / 1024;
+  int request_blocks = (x->home_cap + 511) / 512;
+  if (request_blocks > h->num_sms) request_blocks = h->num_sms;
+
+  // phases 0 / 1: unless this step's prologue was already issued (announced in the previous call, or explicitly)
+  if (phase_lo == 0 && S->pro_route[par] != epoch) {
+    if ((rc = shard_take_epochs(h, st, S->serve_epoch == S->tail_epoch, &S->ep_u[par], &S->ep_i[par])) != ORX_OK) {
+      if (rc == 1) { orx_set_error("orx_shard_step: index epochs are about to wrap; issue this step's route after the previous step's tail"); return ORX_ERR_INVALID; }
+      return rc;
+    }
+    S->ids_u[par] = uid; S->ids_p[par] = pid; S->ids_n[par] = nid; S->ids_B[par] = B;
+  }
+  if (S->pro_route[par] == epoch || phase_lo == 0)      // whichever way the prologue was issued: it must be for THIS batch
+    ORX_REQUIRE(S->ids_u[par] == uid && S->ids_p[par] == pid && S->ids_n[par] == nid && S->ids_B[par] == B,
+                "this step's batch differs from the one its route was issued for (announced as next_* in the previous call)");
+  OrxHash hu = h->pf_u[par];
+  hu.epoch = S->ep_u[par];
+  OrxHash hi = h->hi;
+  hi.epoch = S->ep_i[par];
+
   ShCompArgs ca;
-  ca.U = user->var; ca.Us0 = user->s0; ca.Us1 = user->s1; ca.hu = h->hu; ca.gu = h->gu;
+  ca.U = user->var; ca.Us0 = user->s0; ca.Us1 = user->s1; ca.hu = hu; ca.gu = h->gu;
   ca.margin = margin; ca.c_loss = c_loss; ca.c_l2 = c_l2; ca.inv_B = inv_B; ca.opt = od; ca.partials = h->partials;
   ca.loss_scale = kind == ORX_PAIR_BPR ? inv_B : 1.f;
   ShApplyArgs aa;
   aa.I = item->var; aa.Is0 = item->s0; aa.Is1 = item->s1;
   aa.Bv = item_bias->var; aa.Bs0 = item_bias->s0; aa.Bs1 = item_bias->s1;
-  aa.hi = h->hi; aa.gi = h->gi; aa.gb = h->gb; aa.opt = od;
+  aa.hi = hi; aa.gi = h->gi; aa.gb = h->gb; aa.opt = od;
   const bool whole = phase_lo == 0 && phase_hi == 5;     // the measurement hook follows whole steps only
   for (int ph = phase_lo; ph <= phase_hi; ++ph) {
     if (whole) orx_prof_mark(h, ph, st);
     switch (ph) {
-      case 0:
-        ORX_CUDA(orx_launch_pdl(k_sh_route, dim3((B + 1023) / 1024), dim3(256), 0, st, xd, w, uid, pid, nid, B, total_users,
-                                total_items, epoch));
-        break;
-      case 1: {
-        int g = (x->home_cap + 511) / 512;
-        if (g > h->num_sms * 4) g = h->num_sms * 4;
-        ORX_CUDA(orx_launch_pdl(k_sh_request, dim3(g), dim3(256), 0, st, xd, w, h->hu, epoch));
+      case 0: {
+        if (S->pro_route[par] == epoch) break;           // rode in the previous step's apply launch
+        ShRouteArgs ra;
+        ra.uid = uid; ra.pid = pid; ra.nid = nid; ra.B = B; ra.U = total_users; ra.I = total_items;
+        ORX_CUDA(orx_launch_pdl(k_sh_route, dim3(route_blocks), dim3(256), 0, st, xd, w, ra, epoch));
+        S->pro_route[par] = epoch;
         break;
       }
+      case 1:
+        if (S->pro_request[par] == epoch) break;
+        ORX_REQUIRE(S->pro_route[par] == epoch, "phase 1 before phase 0");
+        ORX_CUDA(orx_launch_pdl(k_sh_request, dim3(request_blocks), dim3(256), 0, st, xd, w, hu, epoch));
+        S->pro_request[par] = epoch;
+        break;
       case 2:
+        ORX_REQUIRE(S->pro_request[par] == epoch, "phase 2 before this step's phases 0 and 1");
 #define SH_SERVE(NQ)                                                                                          \
   ORX_CUDA(orx_launch_pdl(k_sh_serve<NQ>, dim3(h->num_sms * sh_ctas_per_sm((const void*)k_sh_serve<NQ>, 4)),  \
                           dim3(256), 0, st, xd, w, (const float*)item->var, (const float*)item_bias->var,    \
-                          (int64_t)item->rows, h->hi, epoch))
+                          (int64_t)item->rows, hi, epoch))
         if (nq <= 32) SH_SERVE(1); else if (nq <= 64) SH_SERVE(2); else SH_SERVE(4);
 #undef SH_SERVE
+        S->serve_epoch = epoch;
         break;
       case 3:
 #define SH_COMPUTE(K, O) launch_compute<K, O>(nq, h->num_sms, st, xd, w, ca, epoch)
@@ -981,18 +1096,36 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
         }
 #undef SH_COMPUTE
         break;
-      case 4:
-        if (opt->kind == ORX_OPT_SGD) launch_apply<ORX_OPT_SGD>(nq, h->num_sms, st, xd, w, aa, epoch);
-        else if (opt->kind == ORX_OPT_ADAGRAD) launch_apply<ORX_OPT_ADAGRAD>(nq, h->num_sms, st, xd, w, aa, epoch);
-        else launch_apply<ORX_OPT_ADAM_LAZY>(nq, h->num_sms, st, xd, w, aa, epoch);
+      case 4: {
+        ShProArgs pro;
+        memset(&pro, 0, sizeof(pro));
+        const int np = par ^ 1;
+        if (announce && S->pro_route[np] != epoch + 1 &&
+            shard_take_epochs(h, st, false, &S->ep_u[np], &S->ep_i[np]) == ORX_OK) {
+          pro.n_route = (next_B + 1023) / 1024;
+          pro.n_request = request_blocks;
+          pro.epoch = epoch + 1;
+          pro.r.uid = next_uid; pro.r.pid = next_pid; pro.r.nid = next_nid; pro.r.B = next_B;
+          pro.r.U = total_users; pro.r.I = total_items;
+          pro.hu = h->pf_u[np];
+          pro.hu.epoch = S->ep_u[np];
+          S->ids_u[np] = next_uid; S->ids_p[np] = next_pid; S->ids_n[np] = next_nid; S->ids_B[np] = next_B;
+          S->pro_route[np] = S->pro_request[np] = epoch + 1;
+        }
+        if (opt->kind == ORX_OPT_SGD) launch_apply<ORX_OPT_SGD>(nq, h->num_sms, st, xd, w, aa, pro, epoch);
+        else if (opt->kind == ORX_OPT_ADAGRAD) launch_apply<ORX_OPT_ADAGRAD>(nq, h->num_sms, st, xd, w, aa, pro, epoch);
+        else launch_apply<ORX_OPT_ADAM_LAZY>(nq, h->num_sms, st, xd, w, aa, pro, epoch);
         break;
+      }
       case 5: {
         const int g = h->num_sms * 4;
         ShTailArgs ta;
-        ta.U = user->var; ta.Us0 = user->s0; ta.Us1 = user->s1; ta.hu = h->hu; ta.gu = h->gu;
-        if (opt->kind == ORX_OPT_SGD) ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_SGD>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, h->counters, out4));
-        else if (opt->kind == ORX_OPT_ADAGRAD) ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_ADAGRAD>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, h->counters, out4));
-        else ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_ADAM_LAZY>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, h->counters, out4));
+        ta.U = user->var; ta.Us0 = user->s0; ta.Us1 = user->s1; ta.hu = hu; ta.gu = h->gu;
+        int32_t* ticket = h->counters + 2;
+        if (opt->kind == ORX_OPT_SGD) ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_SGD>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, ticket, par, out4));
+        else if (opt->kind == ORX_OPT_ADAGRAD) ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_ADAGRAD>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, ticket, par, out4));
+        else ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_ADAM_LAZY>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, ticket, par, out4));
+        S->tail_epoch = epoch;
         break;
       }
     }

@@ -233,7 +233,8 @@ class HomeRoutedPairwise:
         self._out = torch.zeros(16, 4, dtype=torch.float32, device=dev)     # ring of step outputs
         self._tabs = (eng.make_table(self.user, *self.user_slots), eng.make_table(self.item, *self.item_slots),
                       eng.make_table(self.bias, *self.bias_slots))
-        self.launches_per_step = 6
+        self.launches_per_step = 6      # 4 when every step announces the next batch (step(next_ids=...))
+        self._announced = None
 
     def _set_pointers(self, ptrs):
         self._ptrs = torch.from_numpy(np.ascontiguousarray(ptrs)).to(self.eng.device)
@@ -244,27 +245,37 @@ class HomeRoutedPairwise:
     def _flags(self):
         return self._bufs[7].t if self._bufs is not None else self._tensors[7]
 
-    def _call(self, uid, pid, nid, c_loss, c_l2, lo, hi):
+    def _call(self, uid, pid, nid, c_loss, c_l2, lo, hi, nxt=None, epoch=None):
         eng = self.eng
         B = uid.numel()
         if B > self.B:
             raise ValueError("batch larger than the mailboxes this model was built for")
-        out4 = self._out[self.iterations % 16]
-        o = eng.make_opt(self.opt_kind, self.lr, self.eps, self.b1, self.b2, self.iterations)
+        epoch = self.iterations if epoch is None else epoch
+        out4 = self._out[epoch % 16]
+        o = eng.make_opt(self.opt_kind, self.lr, self.eps, self.b1, self.b2, epoch)
         vp = lambda t: C.c_void_p(t.data_ptr())
+        nx = (vp(nxt[0]), vp(nxt[1]), vp(nxt[2]), nxt[0].numel()) if nxt is not None else (None, None, None, 0)
         _lib.check(eng.lib.orx_shard_step(eng.h, self.kind, C.byref(self._x), C.byref(self._tabs[0]), C.byref(self._tabs[1]),
-                                          C.byref(self._tabs[2]), vp(uid), vp(pid), vp(nid), B, self.U, self.I, self.margin,
-                                          c_loss, c_l2, 1.0 / (B * self.world), C.byref(o), self.iterations, lo, hi, vp(out4),
+                                          C.byref(self._tabs[2]), vp(uid), vp(pid), vp(nid), B, *nx, self.U, self.I, self.margin,
+                                          c_loss, c_l2, 1.0 / (B * self.world), C.byref(o), epoch, lo, hi, vp(out4),
                                           eng.stream()), "orx_shard_step")
         return out4
 
-    def step(self, uid, pid, nid, c_loss=1.0, c_l2=1.0, reduce_loss=True):
+    def step(self, uid, pid, nid, c_loss=1.0, c_l2=1.0, reduce_loss=True, next_ids=None):
         """uid/pid/nid: this rank's int32 GLOBAL ids on the device (every rank must pass the same batch size).
-        Returns a [2] device tensor = the GLOBAL (loss, l2_loss): the partials ride the meta mailboxes."""
+        Returns a [2] device tensor = the GLOBAL (loss, l2_loss): the partials ride the meta mailboxes.
+
+        ``next_ids=(uid, pid, nid)`` announces the batch of the NEXT step (device tensors; the next call must pass these
+        very tensors): its routing and request phases -- two of the four cross-rank handoffs of a step -- then run inside
+        this step's apply launch, and the next step is four launches instead of six.  All ranks announce, or none."""
         if self._loop is not None:
             raise RuntimeError("loopback ranks are stepped by their LoopbackGroup")
+        if self._announced is not None and any(a.data_ptr() != b.data_ptr() for a, b in zip(self._announced, (uid, pid, nid))):
+            raise ValueError("this batch is not the one announced with next_ids= in the previous step")
         self.iterations += 1
-        return self._call(uid, pid, nid, c_loss, c_l2, 0, 5)[:2]
+        out = self._call(uid, pid, nid, c_loss, c_l2, 0, 5, nxt=next_ids)[:2]
+        self._announced = tuple(next_ids) if next_ids is not None else None     # also keeps the tensors alive
+        return out
 
     def check(self):
         """Raise if a flag wait timed out or a mailbox overflowed (sticky device word; one tiny D2H read)."""
@@ -348,6 +359,7 @@ class LoopbackGroup:
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.world = world
         self.ranks = []
+        self._announced = None
         self._engines = [native.Engine(dev.index or 0) for _ in range(world)]
         for r in range(world):
             HomeRoutedPairwise(self._engines[r], r, world, total_users, total_items, dim, batch, peers=self, **kw)
@@ -362,14 +374,27 @@ class LoopbackGroup:
     def _register(self, m):
         self.ranks.append(m)
 
-    def step(self, batches, c_loss=1.0, c_l2=1.0):
-        """batches[r] = (uid, pid, nid) of rank r.  Returns the [2] global (loss, l2_loss) tensor of every rank."""
+    def step(self, batches, c_loss=1.0, c_l2=1.0, next_batches=None):
+        """batches[r] = (uid, pid, nid) of rank r.  Returns the [2] global (loss, l2_loss) tensor of every rank.
+        ``next_batches`` announces the next step's batches: their route / request phases are issued between compute and
+        apply of this step -- where the multi-GPU step runs them (inside the apply launch; fused roles of R virtual ranks
+        on one stream would wait for each other, so the loopback issues the stand-alone kernels at that point)."""
+        if self._announced is not None:
+            for b, a in zip(batches, self._announced):
+                if any(x.data_ptr() != y.data_ptr() for x, y in zip(b, a)):
+                    raise ValueError("these batches are not the ones announced in the previous step")
         for m in self.ranks:
             m.iterations += 1
         outs = [None] * self.world
-        for ph in range(6):
+        for ph in range(6):       # phases 0 / 1 of an announced batch were issued a step ago: the C call skips them
+            fused = ph == 4 and next_batches is not None and self.world == 1    # one rank: the real fused launch
+            if ph == 4 and next_batches is not None and not fused:
+                for early in (0, 1):
+                    for r, m in enumerate(self.ranks):
+                        m._call(*next_batches[r], c_loss, c_l2, early, early, epoch=m.iterations + 1)
             for r, m in enumerate(self.ranks):
-                outs[r] = m._call(*batches[r], c_loss, c_l2, ph, ph)
+                outs[r] = m._call(*batches[r], c_loss, c_l2, ph, ph, nxt=next_batches[r] if fused else None)
+        self._announced = [tuple(b) for b in next_batches] if next_batches is not None else None
         return [o[:2] for o in outs]
 
     def load_global(self, user, item, bias):
@@ -417,18 +442,63 @@ def bench(args, rank, world, eng, barrier, clocks=None):
                 for _ in range(B.N_BATCHES)]
     dev_ids = [tuple(x.to(dev) for x in b) for b in host_ids]
 
+    # Every step announces the next batch (HomeRoutedPairwise.step(next_ids=...)): a training loop knows it -- the data
+    # pipeline is a step ahead -- and the routing + request phases of step t+1 then hide under the apply phase of step t.
+    # ORX_SHARD_ANNOUNCE=0 measures the six-launch step without it.
+    announce = mode == "home" and os.environ.get("ORX_SHARD_ANNOUNCE", "1") != "0"
+    NB = B.N_BATCHES
+    cnt = {"k": 0}
+
     def step(i):
-        model.step(*dev_ids[i % B.N_BATCHES], reduce_loss=False)
+        k = cnt["k"]
+        cnt["k"] = k + 1
+        if announce:
+            model.step(*dev_ids[k % NB], reduce_loss=False, next_ids=dev_ids[(k + 1) % NB])
+        else:
+            model.step(*dev_ids[k % NB], reduce_loss=False)
+
+    def drain():            # the batch announced by the last step of a loop is stepped outside the timed region
+        if announce and model._announced is not None:
+            model.step(*model._announced)
+            cnt["k"] += 1
 
     for i in range(W):
         step(i)
     seconds = B._timed(step, K, barrier, torch, clocks)
-    # e2e: pinned host ids in, global loss out to the host, every step (read one step behind, so the copy overlaps)
+    drain()
+    # e2e: pinned host ids in, global loss out to the host, every step (read one step behind, so the copy overlaps).
+    # The ids of batch k+2 are uploaded on a side stream during step k into a 4-deep ring of device buffers.
     pinned = [torch.zeros(2).pin_memory() for _ in range(2)]
     state = {"prev": None, "last": None}
+    ring = [tuple(torch.empty(Bsz, dtype=torch.int32, device=dev) for _ in range(3)) for _ in range(4)]
+    up_ev, done_ev = [None] * 4, [None] * 4
+    side = torch.cuda.Stream(device=dev)
+    e2e = {"k": 0}
+
+    def upload(k):
+        if done_ev[k % 4] is not None:
+            side.wait_event(done_ev[k % 4])          # the step that last read this ring slot (batch k - 4) has finished
+        with torch.cuda.stream(side):
+            for dst, src in zip(ring[k % 4], host_ids[k % NB]):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        up_ev[k % 4] = ev
 
     def e2e_step(i):
-        out = model.step(*(x.to(dev, non_blocking=True) for x in host_ids[i % B.N_BATCHES]))   # global (loss, l2)
+        k = e2e["k"]
+        e2e["k"] = k + 1
+        if k == 0:
+            upload(0)
+            upload(1)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(up_ev[k % 4])
+        cur.wait_event(up_ev[(k + 1) % 4])
+        out = model.step(*ring[k % 4], next_ids=ring[(k + 1) % 4]) if announce else model.step(*ring[k % 4])   # global (loss, l2)
+        d = torch.cuda.Event()
+        d.record()
+        done_ev[k % 4] = d
+        upload(k + 2)
         pinned[i & 1].copy_(out, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -440,6 +510,7 @@ def bench(args, rank, world, eng, barrier, clocks=None):
     for i in range(W):
         e2e_step(i)
     e2e_seconds = B._timed(e2e_step, K, barrier, torch, clocks)
+    drain()
     state["prev"][0].synchronize()
     last = state["prev"][1].clone()
     if hasattr(model, "check"):
@@ -457,7 +528,8 @@ def bench(args, rank, world, eng, barrier, clocks=None):
                 "note": f"per-GPU per-direction NVLink bytes of the item-row + gradient-row exchange ({rows_each_way} rows each way "
                         f"per triplet, (N-1)/N of them remote) over the WHOLE step time ({ms:.3f} ms): the step also does the local "
                         "HBM work of the single-GPU step; the N = 1 line carries the HBM roofline of the fused kernel"}
-    return {"seconds": seconds, "e2e_seconds": e2e_seconds, "launches": model.launches_per_step * K * world,
+    per_step = 4 if announce else model.launches_per_step
+    return {"seconds": seconds, "e2e_seconds": e2e_seconds, "launches": per_step * K * world,
             "units_per_step": Bsz, "h2d": 3 * 4 * Bsz, "d2h": 8, "roofline": roofline,
             "e2e_api": f"openrec_b200.sharded.{type(model).__name__}.step; pinned host ids in, global loss to host each step",
             "extra": {"last_loss": [float(x) for x in last], "total_items": I, "total_users": U,

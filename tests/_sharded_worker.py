@@ -32,16 +32,23 @@ def main():
     U, I, D, B = (61, 83, 16, 40) if not on_gpu else (1501, 2003, 128, 1024)
     sc = 0.05 if kind == 0 else 0.4
     user, item, bias = (rng.uniform(-sc, sc, s).astype(np.float32) for s in ((U, D), (I, D), (I, 1)))
-    if mode == "home":   # peer-store mailboxes, home-routed (csrc/orx_shard.cu)
+    if mode in ("home", "home_next"):   # peer-store mailboxes, home-routed (csrc/orx_shard.cu)
         m = HomeRoutedPairwise(engine, rank, world, U, I, D, B, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
     else:                # NCCL / gloo all-to-all form
         m = ShardedPairwise(engine, rank, world, U, I, D, kind=kind, opt_kind=opt_kind, lr=0.05, init=False)
     m.load_global(user, item, bias)
     losses = []
-    for step in range(3):
+    steps = 5 if mode == "home_next" else 3
+    batches = []
+    for step in range(steps):
         ids = [rng.integers(0, n, B * world).astype(np.int32) for n in (U, I, I)]   # global batch
-        mine = [torch.from_numpy(a[rank * B:(rank + 1) * B].copy()).to(dev) for a in ids]
-        losses.append(m.step(*mine).cpu().numpy().copy())
+        batches.append([torch.from_numpy(a[rank * B:(rank + 1) * B].copy()).to(dev) for a in ids])
+    for step in range(steps):
+        if mode == "home_next":   # the next batch announced a step ahead: its route / request ride in this step's apply launch
+            nxt = batches[step + 1] if step + 1 < steps and step != 2 else None
+            losses.append(m.step(*batches[step], next_ids=nxt).cpu().numpy().copy())
+        else:
+            losses.append(m.step(*batches[step]).cpu().numpy().copy())
     full = [t.cpu().numpy() for t in m.gather_global()]
     if rank == 0:
         np.savez(out_path, user=full[0], item=full[1], bias=full[2], losses=np.stack(losses))

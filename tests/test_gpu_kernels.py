@@ -426,37 +426,45 @@ def test_dense_apply_and_fill(eng):
     assert torch.equal(t, t2)
 
 
-def test_full_size_bpr_adagrad(eng):
-    """BASELINE.json configs[1]: 1M x 1M, D=128, B=65536; oracle on the touched rows."""
+@pytest.mark.parametrize("kind", ["bpr", "ucml"])
+def test_full_size_pairwise_adagrad(eng, kind):
+    """BASELINE.json configs[1] (BPR) and configs[2] (UCML, margin 0.5, censor_vec after the step): 1M x 1M, D=128,
+    B=65536; oracle on the touched rows, untouched rows bit-identical."""
     from openrec_b200 import native as N
     U = I = 1_000_000
     D, B = 128, 65536
+    scale = 0.05 if kind == "bpr" else 0.4        # ucml: rows longer than 1 so that the censor has work
     tu, ti = torch.empty(U, D, device="cuda"), torch.empty(I, D, device="cuda")
     tb = torch.empty(I, 1, device="cuda")
-    eng.fill_uniform(tu, -0.05, 0.05, 1), eng.fill_uniform(ti, -0.05, 0.05, 2), eng.fill_uniform(tb, -0.05, 0.05, 3)
+    eng.fill_uniform(tu, -scale, scale, 1), eng.fill_uniform(ti, -scale, scale, 2), eng.fill_uniform(tb, -0.05, 0.05, 3)
     au, ai, ab = (torch.full_like(t, 0.1) for t in (tu, ti, tb))
     g = torch.Generator(device="cpu").manual_seed(1)
-    uid, pid, nid = (torch.randint(0, U, (B,), generator=g, dtype=torch.int32) for _ in range(3))
-    rows_u, rows_i = np.unique(uid.numpy()), np.unique(np.concatenate([pid.numpy(), nid.numpy()]))
+    uid, pid, nid = (torch.randint(0, U, (B,), generator=g, dtype=torch.int32).numpy() for _ in range(3))
+    rows_u, rows_i = np.unique(uid), np.unique(np.concatenate([pid, nid]))
     # compact oracle problem over the touched rows only
-    mu = {r: k for k, r in enumerate(rows_u)}
-    mi = {r: k for k, r in enumerate(rows_i)}
-    cu = np.array([mu[r] for r in uid.numpy()], dtype=np.int32)
-    cp = np.array([mi[r] for r in pid.numpy()], dtype=np.int32)
-    cn = np.array([mi[r] for r in nid.numpy()], dtype=np.int32)
+    cu, cp, cn = np.searchsorted(rows_u, uid).astype(np.int32), np.searchsorted(rows_i, pid).astype(np.int32), \
+        np.searchsorted(rows_i, nid).astype(np.int32)
     user = tu[torch.from_numpy(rows_u).cuda()].cpu().numpy().astype(np.float64)
     item = ti[torch.from_numpy(rows_i).cuda()].cpu().numpy().astype(np.float64)
     bias = tb[torch.from_numpy(rows_i).cuda()].cpu().numpy().astype(np.float64)
+    if kind == "ucml":                            # away from the hinge's kink (resampled negatives stay inside rows_i)
+        cn = avoid_hinge_ties(np.random.default_rng(4), user, item, bias, cu, cp, cn).astype(np.int32)
+        nid = rows_i[cn].astype(np.int32)
     st = {k: (np.full_like(v, 0.1), None) for k, v in (("user", user), ("item", item), ("bias", bias))}
     untouched_before = ti[:1000].clone()
     out4 = torch.zeros(4, device="cuda")
-    eng.pairwise_step(N.ORX_PAIR_BPR, N.table(tu, au), N.table(ti, ai), N.table(tb, ab), uid.cuda(), pid.cuda(),
-                      nid.cuda(), N.opt(1, 0.05), out4)
-    loss, l2 = O.pairwise_train_step("bpr", user, item, bias, cu, cp, cn, 1, st, 1, 0.05)
+    k = N.ORX_PAIR_BPR if kind == "bpr" else N.ORX_PAIR_UCML
+    d_uid, d_pid, d_nid = (torch.from_numpy(a).cuda() for a in (uid, pid, nid))
+    eng.pairwise_step(k, N.table(tu, au), N.table(ti, ai), N.table(tb, ab), d_uid, d_pid, d_nid, N.opt(1, 0.05), out4,
+                      margin=0.5)
+    loss, l2 = O.pairwise_train_step(kind, user, item, bias, cu, cp, cn, 1, st, 1, 0.05, margin=0.5)
     close(out4[0], loss, rtol=2e-5), close(out4[1], l2, rtol=2e-5)
-    n_dup = int((np.unique(uid.numpy(), return_counts=True)[1] > 1).sum()
-                + (np.unique(np.concatenate([pid.numpy(), nid.numpy()]), return_counts=True)[1] > 1).sum())
+    n_dup = int((np.unique(uid, return_counts=True)[1] > 1).sum()
+                + (np.unique(np.concatenate([pid, nid]), return_counts=True)[1] > 1).sum())
     assert out4[3].item() == n_dup   # exactly the duplicated rows were staged
+    if kind == "ucml":               # UCML.censor_vec (recommenders/ucml.py:39-46): the caller's three censors after the step
+        eng.censor(tu, d_uid), eng.censor(ti, d_pid), eng.censor(ti, d_nid)
+        O.censor(user, cu), O.censor(item, cp), O.censor(item, cn)
     close(tu[torch.from_numpy(rows_u).cuda()], user)
     close(ti[torch.from_numpy(rows_i).cuda()], item)
     close(tb[torch.from_numpy(rows_i).cuda()], bias)

@@ -19,7 +19,7 @@ def _oracle_state(user, item, bias, opt_kind):
     return {k: (np.zeros_like(v), np.zeros_like(v)) for k, v in zip(("user", "item", "bias"), (user, item, bias))}
 
 
-def _run(world, kind, opt_kind, U, I, D, B, steps=3, bad=False, seed=5):
+def _run(world, kind, opt_kind, U, I, D, B, steps=3, bad=False, seed=5, announce=False):
     from openrec_b200.sharded import LoopbackGroup
     rng = np.random.default_rng(seed)
     sc = 0.05 if kind == 0 else 0.4
@@ -29,15 +29,22 @@ def _run(world, kind, opt_kind, U, I, D, B, steps=3, bad=False, seed=5):
         g.load_global(user, item, bias)
         st = _oracle_state(user, item, bias, opt_kind)
         oracle_opt = {0: O.OPT_SGD, 1: O.OPT_ADAGRAD, 2: O.OPT_ADAM_LAZY}[opt_kind]
+        all_ids, all_batches = [], []
         for step in range(steps):
             ids = [rng.integers(0, n, B * world).astype(np.int32) for n in (U, I, I)]
             if bad:                                  # a few triplets carry an id out of range: skipped as a whole
                 ids[0][3] = -1
-                ids[1][B + 1] = I
+                ids[1][(B + 1) % (B * world)] = I
                 ids[2][2 * B - 1 if world > 1 else 5] = -7
+            all_ids.append(ids)
+            all_batches.append([tuple(torch.from_numpy(a[r * B:(r + 1) * B].copy()).cuda() for a in ids) for r in range(world)])
+        for step in range(steps):
+            ids, batches = all_ids[step], all_batches[step]
             ok = (ids[0] >= 0) & (ids[0] < U) & (ids[1] >= 0) & (ids[1] < I) & (ids[2] >= 0) & (ids[2] < I)
-            batches = [tuple(torch.from_numpy(a[r * B:(r + 1) * B].copy()).cuda() for a in ids) for r in range(world)]
-            outs = [o.cpu().numpy() for o in g.step(batches)]
+            # announce: the next step's route / request are issued inside this step (every second time, so that announced
+            # and plain steps alternate)
+            nxt = all_batches[step + 1] if announce and step + 1 < steps and step % 3 != 2 else None
+            outs = [o.cpu().numpy() for o in g.step(batches, next_batches=nxt)]
             g.check()
             good = [a[ok] for a in ids]
             # BPR's 1/B is over the SUBMITTED batch (skipped triplets still count, as in the single-GPU step)
@@ -79,6 +86,58 @@ def test_loopback_bad_ids():
 
 def test_loopback_eight_ranks():
     _run(8, 0, 1, U=4001, I=9001, D=128, B=2048, steps=2)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("kind,opt_kind", [(0, 1), (1, 2)])
+def test_loopback_announced_batches(world, kind, opt_kind):
+    """The next batch announced a step ahead (its route / request run before this step's apply; world 1 = the fused
+    launch of the multi-GPU step): same results, duplicates across the two steps in flight included."""
+    _run(world, kind, opt_kind, U=151, I=203, D=128, B=512, steps=7, announce=True)
+    _run(world, kind, opt_kind, U=1501, I=2003, D=64, B=1024, steps=5, announce=True, bad=True)
+
+
+def test_announced_batch_must_match():
+    from openrec_b200.sharded import LoopbackGroup
+    g = LoopbackGroup(1, 50, 60, 32, 64, kind=0, opt_kind=1)
+    mk = lambda: [tuple(torch.randint(0, n, (64,), dtype=torch.int32, device="cuda") for n in (50, 60, 60))]
+    try:
+        a, b, c = mk(), mk(), mk()
+        g.step(a, next_batches=b)
+        with pytest.raises(ValueError):
+            g.step(c)
+        g.step(b)
+        g.check()
+    finally:
+        g.close()
+
+
+def test_loopback_index_epoch_wrap():
+    """Index epochs of the sharded step wrap at 2^31 (two per step): tables are emptied at a step boundary, and a batch
+    is not hoisted across the wrap."""
+    from openrec_b200.sharded import LoopbackGroup
+    rng = np.random.default_rng(3)
+    U, I, D, B = 97, 131, 32, 256
+    user, item, bias = (rng.uniform(-0.05, 0.05, s).astype(np.float32).astype(np.float64) for s in ((U, D), (I, D), (I, 1)))
+    g = LoopbackGroup(1, U, I, D, B, kind=0, opt_kind=1, lr=0.05, init=False)
+    try:
+        g.load_global(user, item, bias)
+        st = _oracle_state(user, item, bias, 1)
+        batches = [[tuple(torch.from_numpy(rng.integers(0, n, B).astype(np.int32)).cuda() for n in (U, I, I))] for _ in range(14)]
+        g.step(batches[0])      # builds the workspace
+        O.pairwise_train_step("bpr", user, item, bias, *[t.cpu().numpy() for t in batches[0][0]], O.OPT_ADAGRAD, st, 1, 0.05)
+        m = g.ranks[0]
+        m.eng.debug_set_epoch(0x7fffffff - 24)
+        for k in range(1, 13):
+            g.step(batches[k], next_batches=batches[k + 1])
+            O.pairwise_train_step("bpr", user, item, bias, *[t.cpu().numpy() for t in batches[k][0]], O.OPT_ADAGRAD, st, k + 1, 0.05)
+        g.step(batches[13])
+        O.pairwise_train_step("bpr", user, item, bias, *[t.cpu().numpy() for t in batches[13][0]], O.OPT_ADAGRAD, st, 14, 0.05)
+        g.check()
+        for a, ref in zip([t.cpu().numpy() for t in g.gather_global()], (user, item, bias)):
+            np.testing.assert_allclose(a, ref, atol=1e-5)
+    finally:
+        g.close()
 
 
 def test_shard_checkpoint_roundtrip(tmp_path):

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 # NCCL all-to-all form / home-routed peer-store mailboxes (the 1-GPU form of the latter: test_gpu_shard_loopback.py)
-@pytest.mark.parametrize("mode", ["gpu", "home"])
+@pytest.mark.parametrize("mode", ["gpu", "home", "home_next"])
 @pytest.mark.parametrize("kind,opt_kind", [(0, 1), (0, 0), (1, 1)])
 def test_sharded_step_on_gpus(tmp_path, kind, opt_kind, mode):
     world = min(torch.cuda.device_count(), 4)
@@ -39,7 +39,7 @@ def test_sharded_step_on_gpus(tmp_path, kind, opt_kind, mode):
     user, item, bias = (rng.uniform(-sc, sc, s).astype(np.float32).astype(np.float64) for s in ((U, D), (I, D), (I, 1)))
     st = {k: ((np.full_like(v, 0.1), None) if opt_kind == 1 else (None, None))
           for k, v in zip(("user", "item", "bias"), (user, item, bias))}
-    for step in range(3):
+    for step in range(5 if mode == "home_next" else 3):
         ids = [rng.integers(0, n, B * world).astype(np.int32) for n in (U, I, I)]
         loss, l2 = O.pairwise_train_step("bpr" if kind == 0 else "ucml", user, item, bias, *ids, opt_kind, st,
                                          step + 1, 0.05, margin=0.5)
