@@ -163,3 +163,55 @@ def test_dlrm_training_step(tf, optname, mode):
             close(v.numpy(), ref, atol=2e-5)
     if mode == "dlrm":
         assert np.abs(gr["emb"][0]).max() > 0      # the fixed interaction does train the tables
+
+
+def test_dlrm_full_shape_training_step(tf):
+    """BASELINE.json configs[3]: the Criteo shape (26 tables x 1M x 128, B = 32768, MLPs 13-512-256-128 and
+    479-1024-1024-512-256-1, Adagrad): one training step through the class surface (TMA-fed tcgen05 Dense layers, warp
+    interaction kernels, strided gathers / sparse applies) against the float64 oracle on the touched rows."""
+    from openrec.tf2.recommenders import DLRM
+    rng = np.random.default_rng(33)
+    B, m_spa, T = 32768, 128, 26
+    ln_emb, ln_bot, ln_top = [1_000_000] * T, [512, 256, 128], [1024, 1024, 512, 256, 1]
+    model = DLRM(m_spa=m_spa, ln_emb=ln_emb, ln_bot=ln_bot, ln_top=ln_top, interaction_mode="dlrm")
+    dense = np.log1p(rng.integers(0, 100, (B, 13))).astype(np.float32)
+    sparse = np.stack([rng.integers(0, n, B) for n in ln_emb], 1).astype(np.int64)
+    label = (rng.random(B) < 0.3).astype(np.float32)
+    model._graph(13)
+    tv = model.trainable_variables
+    assert len(tv) == T + 2 * (len(ln_bot) + len(ln_top))
+    rows, csparse, tabs = [], np.zeros_like(sparse), []
+    for k in range(T):                              # compact oracle problem: the touched rows of every table
+        r = np.unique(sparse[:, k])
+        rows.append(r)
+        csparse[:, k] = np.searchsorted(r, sparse[:, k])
+        tabs.append(tv[k].t[torch.from_numpy(r).cuda()].cpu().numpy().astype(np.float64))
+    untouched = [int(np.setdiff1d(np.arange(2000), rows[k])[0]) for k in (0, T - 1)]
+    before = [tv[k].t[u].clone() for k, u in zip((0, T - 1), untouched)]
+    rest = [v.numpy().astype(np.float64) for v in tv[T:]]
+    nb = len(ln_bot)
+    bot_w, bot_b, top_w, top_b = rest[0:2 * nb:2], rest[1:2 * nb:2], rest[2 * nb::2], rest[2 * nb + 1::2]
+    opt = tf.keras.optimizers.Adagrad(learning_rate=0.05)
+    with tf.GradientTape() as tape:
+        loss = model(dense, sparse, label)
+    opt.apply_gradients(zip(tape.gradient(loss, tv), tv))
+    cache = O.dlrm_forward(tabs, bot_w, bot_b, list(top_w), list(top_b), dense.astype(np.float64), csparse,
+                           interaction_mode="dlrm")
+    rl, dpred = O.dlrm_loss(cache["pred"], label, "mse")
+    gr = O.dlrm_backward(cache, tabs, bot_w, list(top_w), dense.astype(np.float64), csparse, dpred, interaction_mode="dlrm")
+    close(float(loss), rl, atol=2e-6)
+    dense_grads = []
+    for l in range(nb):
+        dense_grads += [gr["bot_w"][l], gr["bot_b"][l]]
+    for l in range(len(top_w)):
+        dense_grads += [gr["top_w"][l], gr["top_b"][l]]
+    for j, gd in enumerate(dense_grads):
+        ref = rest[j]
+        O.apply_dense(O.OPT_ADAGRAD, ref, np.full_like(ref, 0.1), None, gd, 1, 0.05)
+        close(tv[T + j].numpy(), ref, atol=2e-5)
+    assert np.abs(gr["emb"][0]).max() > 0
+    for k in (0, 7, T - 1):
+        O.apply_sparse(O.OPT_ADAGRAD, tabs[k], np.full_like(tabs[k], 0.1), None, csparse[:, k], gr["emb"][k], 1, 0.05)
+        close(tv[k].t[torch.from_numpy(rows[k]).cuda()], tabs[k], atol=2e-5)
+    for k, u, b in zip((0, T - 1), untouched, before):
+        assert torch.equal(tv[k].t[u], b)          # rows outside the batch are bit-identical
