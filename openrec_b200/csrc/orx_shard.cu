@@ -448,6 +448,125 @@ k_sh_serve(ShardDev x, ShardWs w, const float* __restrict__ item, const float* _
   if (!EARLY) sh_arrive(x, w.ctl + SH_C_DONE + 2, gridDim.x, 2, epoch, [&]() {});
 }
 
+// ---- early serve, asynchronous form ------------------------------------------------------------------------------
+// The early serve shares the SMs with the apply launch of the step before, which keeps three CTAs per SM and ~94 % of the
+// register file; what is left is ~4 K registers -- but all of the shared memory.  So this form keeps its rows in flight
+// in shared memory instead of registers: 4 warps per CTA, each with a private ring of SLOTS groups of 8 rows; a group is
+// gathered with LDGSTS (cp.async, 16 B per lane, any row address) and leaves as ONE bulk store (cp.async.bulk, up to
+// 8 rows = 4 KB contiguous in the home's `got`).  D <= 256; rows of deferred ids travel as whatever the slot held and
+// are overwritten by the late copy (tail of the step before), which is ordered after this kernel.
+#define SH_ASYNC_WARPS 4
+#define SH_ASYNC_RING_BYTES 24576    // per warp
+
+__device__ __forceinline__ uint32_t sh_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(32 * SH_ASYNC_WARPS, 16)
+k_sh_serve_async(ShardDev x, ShardWs w, const float* __restrict__ item, const float* __restrict__ ibias, int64_t rows, OrxHash hi,
+                 OrxHash hprev, int epoch) {
+  extern __shared__ __align__(128) unsigned char ring_all[];
+  __shared__ int32_t rc[SH_MAX_R], goff[SH_MAX_R], gbase[SH_MAX_R + 1];
+  __shared__ int total_sh;
+  __shared__ unsigned long long dst_sh[SH_ASYNC_WARPS][8];
+  __shared__ uint32_t bytes_sh[SH_ASYNC_WARPS][8];
+  const int R = x.world, me = x.rank, D = x.D, nq = D >> 2;
+  const int row_bytes = D * 4, grp_bytes = 8 * row_bytes;
+  int slots = SH_ASYNC_RING_BYTES / grp_bytes;   // >= 3 (D <= 256)
+  if (slots > 6) slots = 6;
+  const int lag = slots - 2;                 // 1..4 groups gathered ahead of the one being stored
+  orx_pdl_wait();
+  sh_wait(x, 1, epoch);
+  if (threadIdx.x == 0) total_sh = sh_serve_layout(x, rc, goff, gbase);
+  __syncthreads();
+  const int total = total_sh;
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < R) x.meta[threadIdx.x][SH_META * me + SH_M_GINBASE] = gbase[threadIdx.x];
+    if (threadIdx.x == 0) w.ctl[SH_C_NREQ] = total;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = gridDim.x * SH_ASYNC_WARPS;
+  unsigned char* ring = ring_all + (size_t)wid * SH_ASYNC_RING_BYTES;
+  const int32_t* box = x.idbox[me];
+  int it = 0;
+  auto store_group = [&](int g) {            // group g of this warp: gathered -> one bulk store to the home
+    const int sl = g % slots;
+    __syncwarp();
+    if (lane == 0 && bytes_sh[wid][sl]) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_sh[wid][sl]),
+                   "r"(sh_smem_u32(ring + (size_t)sl * grp_bytes)), "r"(bytes_sh[wid][sl])
+                   : "memory");
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  };
+  for (int j0 = (blockIdx.x * SH_ASYNC_WARPS + wid) * 8; j0 < total; j0 += nw * 8, ++it) {
+    const int sl = it % slots;
+    // the bulk store that last read this slot (group it - slots, committed two iterations ago) is done reading
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    const int h = sh_bucket_of(gbase, R, j0);
+    const int idx0 = j0 - gbase[h];
+    int32_t my_id = -1;
+    bool valid = false, copy = false;
+    if (lane < 8) {
+      valid = idx0 + lane < rc[h];
+      int32_t id = valid ? __ldcg(box + (int64_t)h * x.req_cap + idx0 + lane) : -1;
+      if (id < 0 || (int64_t)id >= rows) id = -1;
+      my_id = id;
+      copy = valid;
+      if (id >= 0) {
+        int d;
+        if (orx_hash_find(hprev, id, &d) != 0u) {     // the step before is still updating this row: its tail copies it
+          copy = false;
+          w.late[atomicAdd(w.ctl + SH_C_LATE, 1)] = j0 + lane;
+        }
+      }
+    }
+    const unsigned vmask = __ballot_sync(ORX_FULL, valid) & 0xffu;
+    const unsigned cmask = __ballot_sync(ORX_FULL, copy) & 0xffu;
+    unsigned char* slot = ring + (size_t)sl * grp_bytes;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (!((cmask >> k) & 1u)) continue;
+      const int32_t id = __shfl_sync(ORX_FULL, my_id, k);
+      if (id >= 0) {
+        const float* src = item + (int64_t)id * D;
+        for (int e = lane; e < nq; e += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sh_smem_u32(slot + k * row_bytes + e * 16)),
+                       "l"(__cvta_generic_to_global(src + 4 * e))
+                       : "memory");
+      } else {                                         // an id out of range: a zero row, like the register form
+        for (int e = lane; e < nq; e += 32) *reinterpret_cast<float4*>(slot + k * row_bytes + e * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (lane == 0) {
+      dst_sh[wid][sl] = (unsigned long long)__cvta_generic_to_global(x.got[h] + (int64_t)(goff[h] + idx0) * D);
+      bytes_sh[wid][sl] = (uint32_t)(__popc(vmask) * row_bytes);
+    }
+    if (lane < 8) {
+      w.req[j0 + lane] = my_id;
+      if (my_id >= 0) orx_hash_insert(hi, my_id, 0);
+      if (copy) x.gotb[h][goff[h] + idx0 + lane] = my_id >= 0 ? __ldcg(ibias + my_id) : 0.f;
+    }
+    if (it >= lag) {                                   // group it - lag has landed (all but the `lag` newest gathers)
+      switch (lag) {                                   // cp.async.wait_group takes an immediate
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+      }
+      store_group(it - lag);
+    } else if (lane == 0) {
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep one bulk group per iteration (wait_group.read 1 counts them)
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  for (int g = it - lag < 0 ? 0 : it - lag; g < it; ++g) store_group(g);
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  orx_pdl_trigger();
+}
+
 // ---------------------------------------------------------------------------------------
 // phase 3: home: score, user update, item gradient rows -> owners
 // ---------------------------------------------------------------------------------------
@@ -1047,6 +1166,23 @@ static void launch_apply(int nq, int num_sms, int max_ctas, cudaStream_t st, con
 #undef SH_GO
 }
 
+// tuning switches of the early serve (bench A/B): ORX_SH_ASYNC=0 -> register form; ORX_SH_ASYNC_CTAS=n CTAs per SM
+static bool sh_async_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ORX_SH_ASYNC"); v = !(e && e[0] == '0'); }
+  return v != 0;
+}
+static bool sh_early_enabled() {     // ORX_SH_EARLY=0: announced batches hoist route / request only, the serve stays in its step
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ORX_SH_EARLY"); v = !(e && e[0] == '0'); }
+  return v != 0;
+}
+static int sh_async_ctas() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ORX_SH_ASYNC_CTAS"); v = e ? atoi(e) : 1; if (v < 1 || v > 2) v = 1; }
+  return v;
+}
+
 // FULL: one resident wave on `st`, releases flag 2.  EARLY: one CTA per SM (it shares the SMs with the apply launch of the
 // step before), lists the rows that step is updating instead of copying them, releases nothing.
 static int launch_serve(orx_ctx* c, bool early, cudaStream_t st, const ShardDev& xd, const ShardWs& w, const orx_table_t* item,
@@ -1061,6 +1197,14 @@ static int launch_serve(orx_ctx* c, bool early, cudaStream_t st, const ShardDev&
 #define SH_EARLY(NQ) k_sh_serve<NQ, 4, true><<<c->num_sms, 256, 0, st>>>(xd, w, I, Bv, rows, hi, hprev, epoch)
   if (!early) {
     if (nq <= 32) SH_FULL(1); else if (nq <= 64) SH_FULL(2); else SH_FULL(4);
+  } else if (xd.D <= 256 && sh_async_enabled()) {
+    static bool attr_set = false;
+    const int smem = SH_ASYNC_WARPS * SH_ASYNC_RING_BYTES;
+    if (!attr_set) {
+      ORX_CUDA(cudaFuncSetAttribute(k_sh_serve_async, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    k_sh_serve_async<<<c->num_sms * sh_async_ctas(), 32 * SH_ASYNC_WARPS, smem, st>>>(xd, w, I, Bv, rows, hi, hprev, epoch);
   } else {
     if (nq <= 32) SH_EARLY(1); else if (nq <= 64) SH_EARLY(2); else SH_EARLY(4);
   }
@@ -1224,12 +1368,14 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
           S->pro_route[np] = S->pro_request[np] = epoch + 1;
           ORX_CUDA(cudaEventRecord(S->ev_compute, st));      // behind this step's compute
         }
-        // with an early serve beside it the apply launch keeps to two CTAs per SM (the third slot is the serve's)
-        const int cap = fused ? 2 : 4;
+        // The early serve runs beside this launch.  Its asynchronous form needs ~4 K registers per SM and leaves apply its
+        // three CTAs; the register form (D > 256) needs a CTA slot of its own.
+        const bool early_serve = fused && sh_early_enabled();
+        const int cap = (early_serve && !(x->dim <= 256 && sh_async_enabled())) ? 2 : 4;
         if (opt->kind == ORX_OPT_SGD) launch_apply<ORX_OPT_SGD>(nq, h->num_sms, cap, st, xd, w, aa, pro, epoch);
         else if (opt->kind == ORX_OPT_ADAGRAD) launch_apply<ORX_OPT_ADAGRAD>(nq, h->num_sms, cap, st, xd, w, aa, pro, epoch);
         else launch_apply<ORX_OPT_ADAM_LAZY>(nq, h->num_sms, cap, st, xd, w, aa, pro, epoch);
-        if (fused) {
+        if (early_serve) {
           // The announced step's serve, early form, on the side stream: issued AFTER the apply launch, whose first blocks
           // are the route / request roles this serve waits for (flag 1), so those are resident whatever the scheduler
           // does with the rest.  It reads item rows while apply updates others: rows in this step's item index are left

@@ -97,6 +97,12 @@ def test_loopback_announced_batches(world, kind, opt_kind):
     _run(world, kind, opt_kind, U=1501, I=2003, D=64, B=1024, steps=5, announce=True, bad=True)
 
 
+@pytest.mark.parametrize("D", [8, 64, 192, 256, 512])
+def test_loopback_announced_dims(D):
+    # D <= 256: the asynchronous (shared-memory ring) form of the early serve; above: the register form
+    _run(2, 0, 1, U=301, I=407, D=D, B=256, steps=4, announce=True)
+
+
 def test_announced_batch_must_match():
     from openrec_b200.sharded import LoopbackGroup
     g = LoopbackGroup(1, 50, 60, 32, 64, kind=0, opt_kind=1)
