@@ -60,9 +60,7 @@ enum { SH_M_TRIPS = 0,    // triplets r routed to X                             
 // local control words (ShardWs::ctl)
 enum { SH_C_CURH = 0, SH_C_CURO = SH_MAX_R, SH_C_GOFF = 2 * SH_MAX_R, SH_C_RCO = 3 * SH_MAX_R + 1,
        SH_C_DONE = 4 * SH_MAX_R + 1, SH_C_T = SH_C_DONE + 8, SH_C_NREQ = SH_C_T + 1, SH_C_ACUR = SH_C_T + 2,
-       SH_C_LATE = SH_C_T + 3, SH_C_BAD = SH_C_T + 4, SH_C_BAR = SH_C_T + 5, SH_C_WORDS = SH_C_T + 8 };
-// Every step parity (epoch & 1) has its own block of control words, its own `req` list and its own pair of index sets:
-// kernels of step e + 1 (its route / request roles, its early serve) run while apply / tail of step e still use theirs.
+       SH_C_BAD = SH_C_T + 4 /* + step parity */, SH_C_WORDS = SH_C_T + 8 };
 
 struct ShardHost {   // mirrors orx_shard_t (include/orx.h)
   int32_t world, rank, dim, batch_cap, home_cap, req_cap, gin_cap, timeout_ms;
@@ -82,11 +80,10 @@ struct ShardDev {
   int32_t* const* flags;     // [world] int32 [SH_NPH][SH_MAX_R] + error word
 };
 
-struct ShardWs {       // per-handle local scratch, as seen by the kernels of ONE step (parity-selected on the host)
+struct ShardWs {       // per-handle local scratch
   int32_t* trip_u;     // [home_cap]      local user row of home triplet t
   int32_t* slot;       // [2 * home_cap]  (owner << 24 | index in my bucket for that owner) of lookup 2t + q, -1 = dropped
   int32_t* req;        // [gin_cap]       local item row requested as gradient-inbox row j (-1 = padding / invalid)
-  int32_t* late;       // [gin_cap]       inbox rows whose copy the early serve left to the tail of the step before
   int32_t* ctl;        // [SH_C_WORDS]
 };
 
@@ -207,7 +204,7 @@ __device__ __forceinline__ void sh_route_role(const ShardDev& x, const ShardWs& 
         h[k] = u % R;
         uu[k] = u / R; pp[k] = p; nn[k] = n;
       } else {
-        atomicAdd(w.ctl + SH_C_BAD, 1);
+        atomicAdd(w.ctl + SH_C_BAD + (epoch & 1), 1);
       }
     }
     rk[k] = sh_rank_add(cnt, ok ? h[k] : 0, ok);
@@ -341,46 +338,34 @@ __global__ void __launch_bounds__(256) k_sh_request(ShardDev x, ShardWs w, OrxHa
 // ---------------------------------------------------------------------------------------
 // phase 2: owner: requested rows -> homes
 // ---------------------------------------------------------------------------------------
-// where the requests of every home sit in my inbox order (thread 0 fills the shared arrays): rc[h] requests of home h,
-// destined for rows goff[h].. of ITS `got`; they are my gradient-inbox rows gbase[h].. (32-row aligned).  Returns the
-// padded total (0 .. gin_cap).  Deterministic in the meta words, so the tail's late copies recompute the same layout.
-__device__ __forceinline__ int sh_serve_layout(const ShardDev& x, int32_t* rc, int32_t* goff, int32_t* gbase) {
-  const int R = x.world, me = x.rank;
-  const int32_t* m = x.meta[me];
-  int acc = 0;
-  for (int h = 0; h < R; ++h) {
-    int c = __ldcg(m + SH_META * h + SH_M_REQS);
-    c = c < 0 ? 0 : (c > x.req_cap ? x.req_cap : c);
-    int g = __ldcg(m + SH_META * h + SH_M_GOTOFF);
-    if (g < 0 || g + c > x.got_rows) { g = 0; c = 0; }
-    rc[h] = c;
-    goff[h] = g;
-    gbase[h] = acc;
-    acc += (c + 31) & ~31;
-  }
-  gbase[R] = acc;
-  if (acc > x.gin_cap) {              // my gradient inbox cannot take this batch: sticky error, serve what fits
-    atomicCAS(x.flags[me] + SH_ERR_WORD, 0, 4);
-    acc = x.gin_cap & ~31;
-  }
-  return acc;
-}
-
-// ROWS inbox rows per warp iteration.  EARLY = this launch runs beside the apply launch of the step BEFORE (on a second
-// stream): rows that step is updating -- the ones present in its item index `hprev` -- are not copied but listed in
-// w.late; the tail of that step copies them once they are final and releases flag 2.  Everything else a serve does
-// (index insert, req list, inbox bases) happens here either way.  EARLY runs with half the rows in flight so that one
-// CTA of it fits on an SM beside two CTAs of the apply launch.
-template <int NQ, int ROWS, bool EARLY>
-__global__ void __launch_bounds__(EARLY ? 352 : 256, EARLY ? 2 : 1)
-k_sh_serve(ShardDev x, ShardWs w, const float* __restrict__ item, const float* __restrict__ ibias, int64_t rows, OrxHash hi,
-           OrxHash hprev, int epoch) {
+template <int NQ>
+__global__ void __launch_bounds__(256) k_sh_serve(ShardDev x, ShardWs w, const float* __restrict__ item,
+                                                  const float* __restrict__ ibias, int64_t rows, OrxHash hi, int epoch) {
   __shared__ int32_t rc[SH_MAX_R], goff[SH_MAX_R], gbase[SH_MAX_R + 1];
   __shared__ int total_sh;
   const int R = x.world, me = x.rank, D = x.D, nq = D >> 2;
   orx_pdl_wait();
   sh_wait(x, 1, epoch);
-  if (threadIdx.x == 0) total_sh = sh_serve_layout(x, rc, goff, gbase);
+  if (threadIdx.x == 0) {
+    const int32_t* m = x.meta[me];
+    int acc = 0;
+    for (int h = 0; h < R; ++h) {
+      int c = __ldcg(m + SH_META * h + SH_M_REQS);
+      c = c < 0 ? 0 : (c > x.req_cap ? x.req_cap : c);
+      int g = __ldcg(m + SH_META * h + SH_M_GOTOFF);
+      if (g < 0 || g + c > x.got_rows) { g = 0; c = 0; }
+      rc[h] = c;
+      goff[h] = g;
+      gbase[h] = acc;
+      acc += (c + 31) & ~31;
+    }
+    gbase[R] = acc;
+    if (acc > x.gin_cap) {              // my gradient inbox cannot take this batch: sticky error, serve what fits
+      atomicCAS(x.flags[me] + SH_ERR_WORD, 0, 4);
+      acc = x.gin_cap & ~31;
+    }
+    total_sh = acc;
+  }
   __syncthreads();
   const int total = total_sh;
   if (blockIdx.x == 0) {
@@ -391,52 +376,44 @@ k_sh_serve(ShardDev x, ShardWs w, const float* __restrict__ item, const float* _
   const int nw = (gridDim.x * blockDim.x) >> 5;
   const int32_t* box = x.idbox[me];
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  // a warp moves ROWS consecutive inbox rows per iteration (same source: bases are multiples of 32): lanes 0..ROWS-1
-  // resolve ids, index them and move the biases (one run); then all rows are loaded before the first peer store
-  for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ROWS; j0 < total; j0 += nw * ROWS) {
+  // a warp moves 8 consecutive inbox rows per iteration (same source: bases are multiples of 32): lanes 0..7 resolve
+  // ids, index them and move the biases (one 32 B run); then all 8 rows are loaded before the first peer store
+  for (int j0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 8; j0 < total; j0 += nw * 8) {
     const int h = sh_bucket_of(gbase, R, j0);
     const int idx0 = j0 - gbase[h];
     if (idx0 >= rc[h]) {                 // pure padding
-      if (lane < ROWS) w.req[j0 + lane] = -1;
+      if (lane < 8) w.req[j0 + lane] = -1;
       continue;
     }
     int32_t my_id = -1;
-    bool valid = false, copy = false;
-    if (lane < ROWS) {
+    bool valid = false;
+    if (lane < 8) {
       valid = idx0 + lane < rc[h];
       int32_t id = valid ? __ldcg(box + (int64_t)h * x.req_cap + idx0 + lane) : -1;
       if (id < 0 || (int64_t)id >= rows) id = -1;
       my_id = id;
-      copy = valid;
-      if (EARLY && id >= 0) {            // a row the step before is still updating: its copy waits for that step's tail
-        int d;
-        if (orx_hash_find(hprev, id, &d) != 0u) {
-          copy = false;
-          w.late[atomicAdd(w.ctl + SH_C_LATE, 1)] = j0 + lane;
-        }
-      }
     }
-    const unsigned cmask = __ballot_sync(ORX_FULL, copy) & ((1u << ROWS) - 1u);
+    const unsigned vmask = __ballot_sync(ORX_FULL, valid) & 0xffu;
     float* dst0 = x.got[h] + (int64_t)(goff[h] + idx0) * D;
-    float4 v[ROWS][NQ];
+    float4 v[8][NQ];
 #pragma unroll
-    for (int k = 0; k < ROWS; ++k) {     // all rows in flight before anything that stalls (the index inserts below)
+    for (int k = 0; k < 8; ++k) {     // all eight rows in flight before anything that stalls (the index inserts below)
       const int32_t id = __shfl_sync(ORX_FULL, my_id, k);
-      const bool on = id >= 0 && ((cmask >> k) & 1u);
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int e = q * 32 + lane;
-        v[k][q] = (on && e < nq) ? __ldcg(reinterpret_cast<const float4*>(item + (int64_t)id * D) + e) : z4;
+        v[k][q] = (id >= 0 && e < nq) ? __ldcg(reinterpret_cast<const float4*>(item + (int64_t)id * D) + e) : z4;
       }
     }
-    if (lane < ROWS) {
+    if (lane < 8) {
       w.req[j0 + lane] = my_id;
+      const float b = my_id >= 0 ? __ldcg(ibias + my_id) : 0.f;
       if (my_id >= 0) orx_hash_insert(hi, my_id, 0);
-      if (copy) x.gotb[h][goff[h] + idx0 + lane] = my_id >= 0 ? __ldcg(ibias + my_id) : 0.f;
+      if (valid) x.gotb[h][goff[h] + idx0 + lane] = b;
     }
 #pragma unroll
-    for (int k = 0; k < ROWS; ++k) {
-      if (!((cmask >> k) & 1u)) continue;
+    for (int k = 0; k < 8; ++k) {
+      if (!((vmask >> k) & 1u)) continue;
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int e = q * 32 + lane;
@@ -445,126 +422,7 @@ k_sh_serve(ShardDev x, ShardWs w, const float* __restrict__ item, const float* _
     }
   }
   orx_pdl_trigger();
-  if (!EARLY) sh_arrive(x, w.ctl + SH_C_DONE + 2, gridDim.x, 2, epoch, [&]() {});
-}
-
-// ---- early serve, asynchronous form ------------------------------------------------------------------------------
-// The early serve shares the SMs with the apply launch of the step before, which keeps three CTAs per SM and ~94 % of the
-// register file; what is left is ~4 K registers -- but all of the shared memory.  So this form keeps its rows in flight
-// in shared memory instead of registers: 4 warps per CTA, each with a private ring of SLOTS groups of 8 rows; a group is
-// gathered with LDGSTS (cp.async, 16 B per lane, any row address) and leaves as ONE bulk store (cp.async.bulk, up to
-// 8 rows = 4 KB contiguous in the home's `got`).  D <= 256; rows of deferred ids travel as whatever the slot held and
-// are overwritten by the late copy (tail of the step before), which is ordered after this kernel.
-#define SH_ASYNC_WARPS 4
-#define SH_ASYNC_RING_BYTES 24576    // per warp
-
-__device__ __forceinline__ uint32_t sh_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__global__ void __launch_bounds__(32 * SH_ASYNC_WARPS, 16)
-k_sh_serve_async(ShardDev x, ShardWs w, const float* __restrict__ item, const float* __restrict__ ibias, int64_t rows, OrxHash hi,
-                 OrxHash hprev, int epoch) {
-  extern __shared__ __align__(128) unsigned char ring_all[];
-  __shared__ int32_t rc[SH_MAX_R], goff[SH_MAX_R], gbase[SH_MAX_R + 1];
-  __shared__ int total_sh;
-  __shared__ unsigned long long dst_sh[SH_ASYNC_WARPS][8];
-  __shared__ uint32_t bytes_sh[SH_ASYNC_WARPS][8];
-  const int R = x.world, me = x.rank, D = x.D, nq = D >> 2;
-  const int row_bytes = D * 4, grp_bytes = 8 * row_bytes;
-  int slots = SH_ASYNC_RING_BYTES / grp_bytes;   // >= 3 (D <= 256)
-  if (slots > 6) slots = 6;
-  const int lag = slots - 2;                 // 1..4 groups gathered ahead of the one being stored
-  orx_pdl_wait();
-  sh_wait(x, 1, epoch);
-  if (threadIdx.x == 0) total_sh = sh_serve_layout(x, rc, goff, gbase);
-  __syncthreads();
-  const int total = total_sh;
-  if (blockIdx.x == 0) {
-    if ((int)threadIdx.x < R) x.meta[threadIdx.x][SH_META * me + SH_M_GINBASE] = gbase[threadIdx.x];
-    if (threadIdx.x == 0) w.ctl[SH_C_NREQ] = total;
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int nw = gridDim.x * SH_ASYNC_WARPS;
-  unsigned char* ring = ring_all + (size_t)wid * SH_ASYNC_RING_BYTES;
-  const int32_t* box = x.idbox[me];
-  int it = 0;
-  auto store_group = [&](int g) {            // group g of this warp: gathered -> one bulk store to the home
-    const int sl = g % slots;
-    __syncwarp();
-    if (lane == 0 && bytes_sh[wid][sl]) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_sh[wid][sl]),
-                   "r"(sh_smem_u32(ring + (size_t)sl * grp_bytes)), "r"(bytes_sh[wid][sl])
-                   : "memory");
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  };
-  for (int j0 = (blockIdx.x * SH_ASYNC_WARPS + wid) * 8; j0 < total; j0 += nw * 8, ++it) {
-    const int sl = it % slots;
-    // the bulk store that last read this slot (group it - slots, committed two iterations ago) is done reading
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncwarp();
-    const int h = sh_bucket_of(gbase, R, j0);
-    const int idx0 = j0 - gbase[h];
-    int32_t my_id = -1;
-    bool valid = false, copy = false;
-    if (lane < 8) {
-      valid = idx0 + lane < rc[h];
-      int32_t id = valid ? __ldcg(box + (int64_t)h * x.req_cap + idx0 + lane) : -1;
-      if (id < 0 || (int64_t)id >= rows) id = -1;
-      my_id = id;
-      copy = valid;
-      if (id >= 0) {
-        int d;
-        if (orx_hash_find(hprev, id, &d) != 0u) {     // the step before is still updating this row: its tail copies it
-          copy = false;
-          w.late[atomicAdd(w.ctl + SH_C_LATE, 1)] = j0 + lane;
-        }
-      }
-    }
-    const unsigned vmask = __ballot_sync(ORX_FULL, valid) & 0xffu;
-    const unsigned cmask = __ballot_sync(ORX_FULL, copy) & 0xffu;
-    unsigned char* slot = ring + (size_t)sl * grp_bytes;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (!((cmask >> k) & 1u)) continue;
-      const int32_t id = __shfl_sync(ORX_FULL, my_id, k);
-      if (id >= 0) {
-        const float* src = item + (int64_t)id * D;
-        for (int e = lane; e < nq; e += 32)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sh_smem_u32(slot + k * row_bytes + e * 16)),
-                       "l"(__cvta_generic_to_global(src + 4 * e))
-                       : "memory");
-      } else {                                         // an id out of range: a zero row, like the register form
-        for (int e = lane; e < nq; e += 32) *reinterpret_cast<float4*>(slot + k * row_bytes + e * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    if (lane == 0) {
-      dst_sh[wid][sl] = (unsigned long long)__cvta_generic_to_global(x.got[h] + (int64_t)(goff[h] + idx0) * D);
-      bytes_sh[wid][sl] = (uint32_t)(__popc(vmask) * row_bytes);
-    }
-    if (lane < 8) {
-      w.req[j0 + lane] = my_id;
-      if (my_id >= 0) orx_hash_insert(hi, my_id, 0);
-      if (copy) x.gotb[h][goff[h] + idx0 + lane] = my_id >= 0 ? __ldcg(ibias + my_id) : 0.f;
-    }
-    if (it >= lag) {                                   // group it - lag has landed (all but the `lag` newest gathers)
-      switch (lag) {                                   // cp.async.wait_group takes an immediate
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-      }
-      store_group(it - lag);
-    } else if (lane == 0) {
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep one bulk group per iteration (wait_group.read 1 counts them)
-    }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  for (int g = it - lag < 0 ? 0 : it - lag; g < it; ++g) store_group(g);
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  orx_pdl_trigger();
+  sh_arrive(x, w.ctl + SH_C_DONE + 2, gridDim.x, 2, epoch, [&]() {});
 }
 
 // ---------------------------------------------------------------------------------------
@@ -761,7 +619,6 @@ struct ShProArgs {
   int epoch;                // of the announced step
   ShRouteArgs r;
   OrxHash hu;               // user index of the announced step
-  ShardWs wn;               // scratch of the announced step (other parity)
 };
 
 template <int OPT, int NQ>
@@ -772,12 +629,12 @@ __global__ void __launch_bounds__(256) k_sh_apply(ShardDev x, ShardWs w, ShApply
   const int me = x.rank, D = x.D, nq = D >> 2;
   orx_pdl_wait();
   if ((int)blockIdx.x < pro.n_route) {                    // block-uniform role dispatch
-    sh_route_role(x, pro.wn, pro.r, pro.epoch, blockIdx.x, pro.n_route);
+    sh_route_role(x, w, pro.r, pro.epoch, blockIdx.x, pro.n_route);
     orx_pdl_trigger();
     return;
   }
   if ((int)blockIdx.x < pro.n_route + pro.n_request) {
-    sh_request_role(x, pro.wn, pro.hu, pro.epoch, blockIdx.x - pro.n_route, pro.n_request);
+    sh_request_role(x, w, pro.hu, pro.epoch, blockIdx.x - pro.n_route, pro.n_request);
     orx_pdl_trigger();
     return;
   }
@@ -891,18 +748,9 @@ __device__ __forceinline__ void sh_apply_staged2(float* W, float* P0, float* P1,
   }
 }
 
-// The NEXT step's early serve (k_sh_serve<.., EARLY>) ran beside this step's apply and left the rows this step was
-// updating to us: once every staged row is final (grid barrier -- the grid is one resident wave), copy them to their
-// homes and release that step's flag 2 on behalf of its serve.
-struct ShLateArgs {
-  int enabled;
-  int epoch;          // of the step whose serve we finish
-  ShardWs wn;         // that step's scratch (late list, control words)
-};
-
 template <int OPT>
 __global__ void __launch_bounds__(256) k_sh_tail(ShardDev x, ShardWs w, ShTailArgs u, ShApplyArgs a, int32_t* ticket,
-                                                 ShLateArgs late, float* out4) {
+                                                 int par, float* out4) {
   constexpr bool S0 = (OPT == ORX_OPT_ADAGRAD || OPT == ORX_OPT_ADAM_LAZY);
   constexpr bool S1 = (OPT == ORX_OPT_ADAM_LAZY);
   const int D = x.D;
@@ -938,9 +786,9 @@ __global__ void __launch_bounds__(256) k_sh_tail(ShardDev x, ShardWs w, ShTailAr
     }
     out4[0] = l;
     out4[1] = q;
-    out4[2] = (float)w.ctl[SH_C_BAD];
+    out4[2] = (float)w.ctl[SH_C_BAD + par];
     out4[3] = (float)(nu + ni);
-    w.ctl[SH_C_BAD] = 0;
+    w.ctl[SH_C_BAD + par] = 0;
     w.ctl[SH_C_ACUR] = 0;
   }
   __shared__ bool last;
@@ -955,59 +803,20 @@ __global__ void __launch_bounds__(256) k_sh_tail(ShardDev x, ShardWs w, ShTailAr
     *a.hi.counter = 0;
     *ticket = 0;
   }
-  if (!late.enabled) return;
-  // ---- late copies of the next step's serve
-  __shared__ int32_t rc[SH_MAX_R], goff[SH_MAX_R], gbase[SH_MAX_R + 1];
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(late.wn.ctl + SH_C_BAR, 1);
-    while (*(volatile int32_t*)(late.wn.ctl + SH_C_BAR) < (int)gridDim.x) __nanosleep(32);
-    __threadfence();
-    sh_serve_layout(x, rc, goff, gbase);
-  }
-  __syncthreads();
-  const int n_late = __ldcg(late.wn.ctl + SH_C_LATE);
-  const int R = x.world, nq = D >> 2;
-  for (int i = gwarp; i < n_late; i += nw) {
-    const int j = __ldcg(late.wn.late + i);
-    const int32_t id = __ldcg(late.wn.req + j);
-    const int h = sh_bucket_of(gbase, R, j);
-    const int pos = goff[h] + (j - gbase[h]);
-    if (id < 0) continue;
-    const float4* src = reinterpret_cast<const float4*>(a.I + (int64_t)id * D);
-    float4* dst = reinterpret_cast<float4*>(x.got[h] + (int64_t)pos * D);
-    for (int e = lane; e < nq; e += 32) dst[e] = __ldcg(src + e);
-    if (lane == 0) x.gotb[h][pos] = __ldcg(a.Bv + id);
-  }
-  sh_arrive(x, late.wn.ctl + SH_C_DONE + 2, gridDim.x, 2, late.epoch, [&]() {
-    if (threadIdx.x == 0) {
-      late.wn.ctl[SH_C_LATE] = 0;
-      late.wn.ctl[SH_C_BAR] = 0;
-    }
-  });
 }
 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 struct orx_shard_ws {
-  int32_t *trip_u, *slot, *req, *late, *ctl;     // device scratch; req / late / ctl hold one copy per step parity
+  ShardWs w;
   int home_cap, gin_cap, got_rows;
-  cudaStream_t side;                             // the next step's early serve runs here, beside this step's apply
-  cudaEvent_t ev_compute, ev_serve;
-  // bookkeeping, per step parity: which step's route / request / serve were issued, with which index epochs and ids
-  int32_t pro_route[2], pro_request[2], served[2], early[2];
+  // prologue bookkeeping, per step parity: which step's route / request were issued, with which index epochs and ids
+  int32_t pro_route[2], pro_request[2];
   uint32_t ep_u[2], ep_i[2];
   const int32_t *ids_u[2], *ids_p[2], *ids_n[2];
   int32_t ids_B[2];
-  int32_t max_served, tail_epoch;                // newest step with a serve issued / with its tail issued
-
-  ShardWs view(int par) const {
-    ShardWs w;
-    w.trip_u = trip_u; w.slot = slot;
-    w.req = req + (size_t)par * gin_cap; w.late = late + (size_t)par * gin_cap; w.ctl = ctl + par * SH_C_WORDS;
-    return w;
-  }
+  int32_t serve_epoch, tail_epoch;   // last step whose serve / tail was issued (different = a step's item index is live)
 };
 
 // ---- IPC-exportable device memory: every rank maps every other rank's mailboxes (cudaIpc*, one box, NVLink) ----
@@ -1065,14 +874,10 @@ static int sh_ctas_per_sm(const void* fn, int cap) {
 static void shard_ws_free(orx_ctx* c) {
   orx_shard_ws* s = (orx_shard_ws*)c->shard_ws;
   if (!s) return;
-  cudaFree(s->trip_u);
-  cudaFree(s->slot);
-  cudaFree(s->req);
-  cudaFree(s->late);
-  cudaFree(s->ctl);
-  if (s->side) cudaStreamDestroy(s->side);
-  if (s->ev_compute) cudaEventDestroy(s->ev_compute);
-  if (s->ev_serve) cudaEventDestroy(s->ev_serve);
+  cudaFree(s->w.trip_u);
+  cudaFree(s->w.slot);
+  cudaFree(s->w.req);
+  cudaFree(s->w.ctl);
   delete s;
   c->shard_ws = nullptr;
 }
@@ -1083,21 +888,16 @@ static int shard_ws_ensure(orx_ctx* c, const ShardHost* x, cudaStream_t st) {
   orx_shard_ws* s = (orx_shard_ws*)c->shard_ws;
   const int got_rows = sh_got_rows(x->home_cap, x->world);
   if (s && s->home_cap >= x->home_cap && s->gin_cap >= x->gin_cap && s->got_rows >= got_rows) return ORX_OK;
-  ORX_CUDA(cudaDeviceSynchronize());
+  ORX_CUDA(cudaStreamSynchronize(st));
   shard_ws_free(c);
   s = new orx_shard_ws();
   memset(s, 0, sizeof(*s));
   c->shard_ws = s;
-  ORX_CUDA(cudaMalloc(&s->trip_u, sizeof(int32_t) * (size_t)x->home_cap));
-  ORX_CUDA(cudaMalloc(&s->slot, sizeof(int32_t) * 2 * (size_t)x->home_cap));
-  ORX_CUDA(cudaMalloc(&s->req, sizeof(int32_t) * 2 * (size_t)x->gin_cap));
-  ORX_CUDA(cudaMalloc(&s->late, sizeof(int32_t) * 2 * (size_t)x->gin_cap));
-  ORX_CUDA(cudaMalloc(&s->ctl, sizeof(int32_t) * 2 * SH_C_WORDS));
-  ORX_CUDA(cudaMemsetAsync(s->ctl, 0, sizeof(int32_t) * 2 * SH_C_WORDS, st));
-  ORX_CUDA(cudaStreamSynchronize(st));
-  ORX_CUDA(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
-  ORX_CUDA(cudaEventCreateWithFlags(&s->ev_compute, cudaEventDisableTiming));
-  ORX_CUDA(cudaEventCreateWithFlags(&s->ev_serve, cudaEventDisableTiming));
+  ORX_CUDA(cudaMalloc(&s->w.trip_u, sizeof(int32_t) * (size_t)x->home_cap));
+  ORX_CUDA(cudaMalloc(&s->w.slot, sizeof(int32_t) * 2 * (size_t)x->home_cap));
+  ORX_CUDA(cudaMalloc(&s->w.req, sizeof(int32_t) * (size_t)x->gin_cap));
+  ORX_CUDA(cudaMalloc(&s->w.ctl, sizeof(int32_t) * SH_C_WORDS));
+  ORX_CUDA(cudaMemsetAsync(s->w.ctl, 0, sizeof(int32_t) * SH_C_WORDS, st));
   s->home_cap = x->home_cap;
   s->gin_cap = x->gin_cap;
   s->got_rows = got_rows;
@@ -1155,63 +955,15 @@ static int launch_compute(int nq, int num_sms, cudaStream_t st, const ShardDev& 
 #undef SH_GO
 }
 template <int OPT>
-static void launch_apply(int nq, int num_sms, int max_ctas, cudaStream_t st, const ShardDev& xd, const ShardWs& w,
-                         const ShApplyArgs& a, const ShProArgs& pro, int epoch) {
+static void launch_apply(int nq, int num_sms, cudaStream_t st, const ShardDev& xd, const ShardWs& w, const ShApplyArgs& a,
+                         const ShProArgs& pro, int epoch) {
 #define SH_GO(NQ)                                                                          \
   {                                                                                        \
-    const int g = num_sms * sh_ctas_per_sm((const void*)k_sh_apply<OPT, NQ>, max_ctas) + pro.n_route + pro.n_request; \
+    const int g = num_sms * sh_ctas_per_sm((const void*)k_sh_apply<OPT, NQ>, 4) + pro.n_route + pro.n_request; \
     orx_launch_pdl(k_sh_apply<OPT, NQ>, dim3(g), dim3(256), 0, st, xd, w, a, pro, epoch);  \
   }
   if (nq <= 32) SH_GO(1) else if (nq <= 64) SH_GO(2) else SH_GO(4)
 #undef SH_GO
-}
-
-// tuning switches of the early serve (bench A/B): ORX_SH_ASYNC=0 -> register form; ORX_SH_ASYNC_CTAS=n CTAs per SM
-static bool sh_async_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ORX_SH_ASYNC"); v = !(e && e[0] == '0'); }
-  return v != 0;
-}
-static bool sh_early_enabled() {     // ORX_SH_EARLY=0: announced batches hoist route / request only, the serve stays in its step
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ORX_SH_EARLY"); v = !(e && e[0] == '0'); }
-  return v != 0;
-}
-static int sh_async_ctas() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("ORX_SH_ASYNC_CTAS"); v = e ? atoi(e) : 1; if (v < 1 || v > 2) v = 1; }
-  return v;
-}
-
-// FULL: one resident wave on `st`, releases flag 2.  EARLY: one CTA per SM (it shares the SMs with the apply launch of the
-// step before), lists the rows that step is updating instead of copying them, releases nothing.
-static int launch_serve(orx_ctx* c, bool early, cudaStream_t st, const ShardDev& xd, const ShardWs& w, const orx_table_t* item,
-                        const orx_table_t* bias, const OrxHash& hi, const OrxHash& hprev, int epoch) {
-  const int nq = xd.D >> 2;
-  const float* I = item->var;
-  const float* Bv = bias->var;
-  const int64_t rows = item->rows;
-#define SH_FULL(NQ)                                                                                               \
-  ORX_CUDA(orx_launch_pdl(k_sh_serve<NQ, 8, false>, dim3(c->num_sms * sh_ctas_per_sm((const void*)k_sh_serve<NQ, 8, false>, 4)), \
-                          dim3(256), 0, st, xd, w, I, Bv, rows, hi, hprev, epoch))
-#define SH_EARLY(NQ) k_sh_serve<NQ, 4, true><<<c->num_sms, 256, 0, st>>>(xd, w, I, Bv, rows, hi, hprev, epoch)
-  if (!early) {
-    if (nq <= 32) SH_FULL(1); else if (nq <= 64) SH_FULL(2); else SH_FULL(4);
-  } else if (xd.D <= 256 && sh_async_enabled()) {
-    static bool attr_set = false;
-    const int smem = SH_ASYNC_WARPS * SH_ASYNC_RING_BYTES;
-    if (!attr_set) {
-      ORX_CUDA(cudaFuncSetAttribute(k_sh_serve_async, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
-    k_sh_serve_async<<<c->num_sms * sh_async_ctas(), 32 * SH_ASYNC_WARPS, smem, st>>>(xd, w, I, Bv, rows, hi, hprev, epoch);
-  } else {
-    if (nq <= 32) SH_EARLY(1); else if (nq <= 64) SH_EARLY(2); else SH_EARLY(4);
-  }
-#undef SH_FULL
-#undef SH_EARLY
-  ORX_LAUNCH_CHECK();
-  return ORX_OK;
 }
 
 // two fresh index epochs (user set of the step, item set of the step).  A 31-bit wrap empties every table of the handle
@@ -1269,9 +1021,9 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
   if ((rc = orx_ensure_workspace(h, need, x->dim, false))) return rc;
   if ((rc = shard_ws_ensure(h, x, st))) return rc;
   orx_shard_ws* S = (orx_shard_ws*)h->shard_ws;
-  const int par = epoch & 1, np = par ^ 1;
-  const ShardWs w = S->view(par), wn = S->view(np);
+  const ShardWs& w = S->w;
   const ShardDev xd = shard_to_dev(x);
+  const int par = epoch & 1;
   const OrxOptDev od = orx_opt_to_dev(opt);
   const int nq = x->dim >> 2;
   if ((rc = orx_ensure_partials(h, h->num_sms * 4 * 8, st))) return rc;   // compute grid <= 4 CTAs/SM x 8 warps
@@ -1281,7 +1033,7 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
 
   // phases 0 / 1: unless this step's prologue was already issued (announced in the previous call, or explicitly)
   if (phase_lo == 0 && S->pro_route[par] != epoch) {
-    if ((rc = shard_take_epochs(h, st, S->tail_epoch >= S->max_served, &S->ep_u[par], &S->ep_i[par])) != ORX_OK) {
+    if ((rc = shard_take_epochs(h, st, S->serve_epoch == S->tail_epoch, &S->ep_u[par], &S->ep_i[par])) != ORX_OK) {
       if (rc == 1) { orx_set_error("orx_shard_step: index epochs are about to wrap; issue this step's route after the previous step's tail"); return ORX_ERR_INVALID; }
       return rc;
     }
@@ -1290,12 +1042,10 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
   if (S->pro_route[par] == epoch || phase_lo == 0)      // whichever way the prologue was issued: it must be for THIS batch
     ORX_REQUIRE(S->ids_u[par] == uid && S->ids_p[par] == pid && S->ids_n[par] == nid && S->ids_B[par] == B,
                 "this step's batch differs from the one its route was issued for (announced as next_* in the previous call)");
-  // index sets of this step: the handle's sets 1 / 2 by step parity (a handle that runs the sharded step does not also
-  // run orx_pairwise_prefetch, which uses the same sets)
-  OrxHash hu = h->pf_u[par], hi = h->pf_i[par], hi_prev = h->pf_i[np];
+  OrxHash hu = h->pf_u[par];
   hu.epoch = S->ep_u[par];
+  OrxHash hi = h->hi;
   hi.epoch = S->ep_i[par];
-  hi_prev.epoch = S->ep_i[np];
 
   ShCompArgs ca;
   ca.U = user->var; ca.Us0 = user->s0; ca.Us1 = user->s1; ca.hu = hu; ca.gu = h->gu;
@@ -1323,20 +1073,17 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
         ORX_CUDA(orx_launch_pdl(k_sh_request, dim3(request_blocks), dim3(256), 0, st, xd, w, hu, epoch));
         S->pro_request[par] = epoch;
         break;
-      case 2: {
-        if (S->served[par] == epoch) break;              // served early, beside the previous step's apply
+      case 2:
         ORX_REQUIRE(S->pro_request[par] == epoch, "phase 2 before this step's phases 0 and 1");
-        // the step before has been served but not tailed: its item rows are still being updated -> early form
-        const bool early = S->max_served == epoch - 1 && S->tail_epoch < epoch - 1;
-        if ((rc = launch_serve(h, early, st, xd, w, item, item_bias, hi, hi_prev, epoch))) return rc;
-        S->served[par] = epoch;
-        S->early[par] = early ? epoch : 0;
-        S->max_served = epoch;
+#define SH_SERVE(NQ)                                                                                          \
+  ORX_CUDA(orx_launch_pdl(k_sh_serve<NQ>, dim3(h->num_sms * sh_ctas_per_sm((const void*)k_sh_serve<NQ>, 4)),  \
+                          dim3(256), 0, st, xd, w, (const float*)item->var, (const float*)item_bias->var,    \
+                          (int64_t)item->rows, hi, epoch))
+        if (nq <= 32) SH_SERVE(1); else if (nq <= 64) SH_SERVE(2); else SH_SERVE(4);
+#undef SH_SERVE
+        S->serve_epoch = epoch;
         break;
-      }
       case 3:
-        ORX_REQUIRE(S->served[par] == epoch && (S->early[par] != epoch), "phase 3 before this step's serve was completed "
-                    "(an early serve is finished by the previous step's tail)");
 #define SH_COMPUTE(K, O) launch_compute<K, O>(nq, h->num_sms, st, xd, w, ca, epoch)
         if (kind == ORX_PAIR_BPR) {
           if (opt->kind == ORX_OPT_SGD) SH_COMPUTE(ORX_PAIR_BPR, ORX_OPT_SGD);
@@ -1352,10 +1099,9 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
       case 4: {
         ShProArgs pro;
         memset(&pro, 0, sizeof(pro));
-        bool fused = false;
+        const int np = par ^ 1;
         if (announce && S->pro_route[np] != epoch + 1 &&
             shard_take_epochs(h, st, false, &S->ep_u[np], &S->ep_i[np]) == ORX_OK) {
-          fused = true;
           pro.n_route = (next_B + 1023) / 1024;
           pro.n_request = request_blocks;
           pro.epoch = epoch + 1;
@@ -1363,50 +1109,22 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
           pro.r.U = total_users; pro.r.I = total_items;
           pro.hu = h->pf_u[np];
           pro.hu.epoch = S->ep_u[np];
-          pro.wn = wn;
           S->ids_u[np] = next_uid; S->ids_p[np] = next_pid; S->ids_n[np] = next_nid; S->ids_B[np] = next_B;
           S->pro_route[np] = S->pro_request[np] = epoch + 1;
-          ORX_CUDA(cudaEventRecord(S->ev_compute, st));      // behind this step's compute
         }
-        // The early serve runs beside this launch.  Its asynchronous form needs ~4 K registers per SM and leaves apply its
-        // three CTAs; the register form (D > 256) needs a CTA slot of its own.
-        const bool early_serve = fused && sh_early_enabled();
-        const int cap = (early_serve && !(x->dim <= 256 && sh_async_enabled())) ? 2 : 4;
-        if (opt->kind == ORX_OPT_SGD) launch_apply<ORX_OPT_SGD>(nq, h->num_sms, cap, st, xd, w, aa, pro, epoch);
-        else if (opt->kind == ORX_OPT_ADAGRAD) launch_apply<ORX_OPT_ADAGRAD>(nq, h->num_sms, cap, st, xd, w, aa, pro, epoch);
-        else launch_apply<ORX_OPT_ADAM_LAZY>(nq, h->num_sms, cap, st, xd, w, aa, pro, epoch);
-        if (early_serve) {
-          // The announced step's serve, early form, on the side stream: issued AFTER the apply launch, whose first blocks
-          // are the route / request roles this serve waits for (flag 1), so those are resident whatever the scheduler
-          // does with the rest.  It reads item rows while apply updates others: rows in this step's item index are left
-          // to this step's tail (late list).
-          OrxHash hi_next = h->pf_i[np];
-          hi_next.epoch = S->ep_i[np];
-          ORX_CUDA(cudaStreamWaitEvent(S->side, S->ev_compute, 0));
-          if ((rc = launch_serve(h, true, S->side, xd, wn, item, item_bias, hi_next, hi, epoch + 1))) return rc;
-          ORX_CUDA(cudaEventRecord(S->ev_serve, S->side));
-          ORX_CUDA(cudaStreamWaitEvent(st, S->ev_serve, 0));   // in front of the tail, which finishes that serve
-          S->served[np] = S->early[np] = epoch + 1;
-          S->max_served = epoch + 1;
-        }
+        if (opt->kind == ORX_OPT_SGD) launch_apply<ORX_OPT_SGD>(nq, h->num_sms, st, xd, w, aa, pro, epoch);
+        else if (opt->kind == ORX_OPT_ADAGRAD) launch_apply<ORX_OPT_ADAGRAD>(nq, h->num_sms, st, xd, w, aa, pro, epoch);
+        else launch_apply<ORX_OPT_ADAM_LAZY>(nq, h->num_sms, st, xd, w, aa, pro, epoch);
         break;
       }
       case 5: {
+        const int g = h->num_sms * 4;
         ShTailArgs ta;
         ta.U = user->var; ta.Us0 = user->s0; ta.Us1 = user->s1; ta.hu = hu; ta.gu = h->gu;
         int32_t* ticket = h->counters + 2;
-        ShLateArgs la;
-        la.enabled = S->early[np] == epoch + 1;
-        la.epoch = epoch + 1;
-        la.wn = wn;
-#define SH_TAIL(O)                                                                                               \
-  ORX_CUDA(orx_launch_pdl(k_sh_tail<O>, dim3(h->num_sms * sh_ctas_per_sm((const void*)k_sh_tail<O>, 4)), dim3(256), 0, st, \
-                          xd, w, ta, aa, ticket, la, out4))
-        if (opt->kind == ORX_OPT_SGD) SH_TAIL(ORX_OPT_SGD);
-        else if (opt->kind == ORX_OPT_ADAGRAD) SH_TAIL(ORX_OPT_ADAGRAD);
-        else SH_TAIL(ORX_OPT_ADAM_LAZY);
-#undef SH_TAIL
-        if (la.enabled) S->early[np] = 0;                 // completed: that step may compute
+        if (opt->kind == ORX_OPT_SGD) ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_SGD>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, ticket, par, out4));
+        else if (opt->kind == ORX_OPT_ADAGRAD) ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_ADAGRAD>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, ticket, par, out4));
+        else ORX_CUDA(orx_launch_pdl(k_sh_tail<ORX_OPT_ADAM_LAZY>, dim3(g), dim3(256), 0, st, xd, w, ta, aa, ticket, par, out4));
         S->tail_epoch = epoch;
         break;
       }

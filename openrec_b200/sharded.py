@@ -267,8 +267,7 @@ class HomeRoutedPairwise:
 
         ``next_ids=(uid, pid, nid)`` announces the batch of the NEXT step (device tensors; the next call must pass these
         very tensors): its routing and request phases -- two of the four cross-rank handoffs of a step -- then run inside
-        this step's apply launch and its serve phase beside it on a second stream (rows this step is still updating are
-        copied by this step's tail); the next step then starts at compute.  All ranks announce, or none."""
+        this step's apply launch, and the next step is four launches instead of six.  All ranks announce, or none."""
         if self._loop is not None:
             raise RuntimeError("loopback ranks are stepped by their LoopbackGroup")
         if self._announced is not None and any(a.data_ptr() != b.data_ptr() for a, b in zip(self._announced, (uid, pid, nid))):
@@ -377,11 +376,9 @@ class LoopbackGroup:
 
     def step(self, batches, c_loss=1.0, c_l2=1.0, next_batches=None):
         """batches[r] = (uid, pid, nid) of rank r.  Returns the [2] global (loss, l2_loss) tensor of every rank.
-        ``next_batches`` announces the next step's batches: their route / request / early-serve phases are issued between
-        compute and apply of this step -- where the multi-GPU step runs them (roles inside the apply launch and a serve
-        on a second stream; R virtual ranks on one stream would wait for each other, so the loopback issues the
-        stand-alone kernels at that point, which also makes the early serve read every row BEFORE this step's apply:
-        a row it failed to leave to the tail would show up as a parity error)."""
+        ``next_batches`` announces the next step's batches: their route / request phases are issued between compute and
+        apply of this step -- where the multi-GPU step runs them (inside the apply launch; fused roles of R virtual ranks
+        on one stream would wait for each other, so the loopback issues the stand-alone kernels at that point)."""
         if self._announced is not None:
             for b, a in zip(batches, self._announced):
                 if any(x.data_ptr() != y.data_ptr() for x, y in zip(b, a)):
@@ -392,7 +389,7 @@ class LoopbackGroup:
         for ph in range(6):       # phases 0 / 1 of an announced batch were issued a step ago: the C call skips them
             fused = ph == 4 and next_batches is not None and self.world == 1    # one rank: the real fused launch
             if ph == 4 and next_batches is not None and not fused:
-                for early in (0, 1, 2):    # route, request and the early form of serve (rows this step updates: left to its tail)
+                for early in (0, 1):
                     for r, m in enumerate(self.ranks):
                         m._call(*next_batches[r], c_loss, c_l2, early, early, epoch=m.iterations + 1)
             for r, m in enumerate(self.ranks):
