@@ -817,6 +817,7 @@ struct orx_shard_ws {
   const int32_t *ids_u[2], *ids_p[2], *ids_n[2];
   int32_t ids_B[2];
   int32_t serve_epoch, tail_epoch;   // last step whose serve / tail was issued (different = a step's item index is live)
+  const void* owner;                 // the model (its flag mailbox) this bookkeeping belongs to
 };
 
 // ---- IPC-exportable device memory: every rank maps every other rank's mailboxes (cudaIpc*, one box, NVLink) ----
@@ -1021,6 +1022,15 @@ extern "C" int orx_shard_step(orx_handle_t h, int32_t kind, const orx_shard_t* x
   if ((rc = orx_ensure_workspace(h, need, x->dim, false))) return rc;
   if ((rc = shard_ws_ensure(h, x, st))) return rc;
   orx_shard_ws* S = (orx_shard_ws*)h->shard_ws;
+  if (S->owner != x->flags) {        // another model on this handle (each has its own mailboxes): its steps start afresh
+    ORX_REQUIRE(S->serve_epoch == S->tail_epoch && S->pro_route[0] <= S->tail_epoch && S->pro_route[1] <= S->tail_epoch,
+                "another sharded model on this handle has a step in flight or an announced batch outstanding");
+    memset(S->pro_route, 0, sizeof(S->pro_route));
+    memset(S->pro_request, 0, sizeof(S->pro_request));
+    S->serve_epoch = S->tail_epoch = 0;
+    S->owner = x->flags;
+  }
+  ORX_REQUIRE(!h->pf_valid, "this handle has an index prefetched by orx_pairwise_prefetch outstanding (the sharded step uses the same index sets)");
   const ShardWs& w = S->w;
   const ShardDev xd = shard_to_dev(x);
   const int par = epoch & 1;
