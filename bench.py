@@ -657,6 +657,9 @@ def main():
     ap.add_argument("--workload", default="bpr", choices=["bpr", "ucml", "dlrm"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs (profiling runs)")
     ap.add_argument("--no-secondary", action="store_true", help="bpr only: do not append the ucml / dlrm lines")
+    ap.add_argument("--check", action="store_true",
+                    help="--gpus N > 1: after the timed loops run ONE more step on a fresh batch and verify it on rank 0 against "
+                         "the oracle over the rows the global batch touches (tests/shard_check.py); the verdict goes to extra.check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

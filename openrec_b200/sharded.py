@@ -23,6 +23,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -515,6 +516,15 @@ def bench(args, rank, world, eng, barrier, clocks=None):
     last = state["prev"][1].clone()
     if hasattr(model, "check"):
         model.check()
+    checked = None
+    if getattr(args, "check", False):
+        # parity at the full table shape (BASELINE configs[4]); the oracle stays under tests/ (test infrastructure)
+        tests_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests")
+        if tests_dir not in sys.path:
+            sys.path.insert(0, tests_dir)
+        import shard_check
+        access = shard_check.HomeRoutedAccess(model) if mode == "home" else shard_check.CombinedAccess(model)
+        checked = shard_check.run(model, access, rank, world, U, I, D, Bsz, kind=0, opt_kind=1, lr=B.LR)
     # NVLink-bound exchange: bytes per GPU per direction per step: rows out as owner + gradient rows out as home
     rows_each_way = 2 if mode == "home" else 3
     link_bytes = 2.0 * (world - 1) / world * rows_each_way * (D + 1) * 4 * Bsz
@@ -532,7 +542,7 @@ def bench(args, rank, world, eng, barrier, clocks=None):
     return {"seconds": seconds, "e2e_seconds": e2e_seconds, "launches": per_step * K * world,
             "units_per_step": Bsz, "h2d": 3 * 4 * Bsz, "d2h": 8, "roofline": roofline,
             "e2e_api": f"openrec_b200.sharded.{type(model).__name__}.step; pinned host ids in, global loss to host each step",
-            "extra": {"last_loss": [float(x) for x in last], "total_items": I, "total_users": U,
+            "extra": {"last_loss": [float(x) for x in last], "total_items": I, "total_users": U, "check": checked,
                       "exchange": {"home": "home-routed: triplets computed on the user row's owner; item rows / gradient rows "
                                            "as peer stores into IPC-mapped mailboxes over NVLink, flag words instead of "
                                            "barriers, no collective, no host sync",

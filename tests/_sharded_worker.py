@@ -52,6 +52,15 @@ def main():
     full = [t.cpu().numpy() for t in m.gather_global()]
     if rank == 0:
         np.savez(out_path, user=full[0], item=full[1], bias=full[2], losses=np.stack(losses))
+    if mode in ("cpu", "home", "home_next") and opt_kind in (0, 1) and kind == 0:
+        # the touched-rows check that bench.py --gpus N --check runs at the full table shape (tests/shard_check.py):
+        # one more step, verified on rank 0 against the oracle from the shards' own snapshots
+        import shard_check
+        access = shard_check.HomeRoutedAccess(m) if mode != "cpu" else shard_check.CombinedAccess(m)
+        verdict = shard_check.run(m, access, rank, world, U, I, D, B, kind=kind, opt_kind=opt_kind, lr=0.05,
+                                  atol=1e-5 if kind == 0 else 2e-4)
+        if rank == 0:
+            assert verdict["passed"] and verdict["global_batch"] == B * world
     if hasattr(m, "check"):
         m.check()
     if hasattr(m, "close"):
